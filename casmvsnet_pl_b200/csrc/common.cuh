@@ -1,0 +1,65 @@
+// Shared helpers for libcasmvs (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "casmvs.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libcasmvs is written for sm_100a (B200) only"
+#endif
+
+namespace casmvs {
+
+// thread-local error string + process-wide launch counter (api.cu)
+void set_error(const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// call after every kernel launch: counts it and converts launch errors
+inline int after_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+    return -2;
+  }
+  return 0;
+}
+
+#define CASMVS_REQUIRE(cond, ...)        \
+  do {                                   \
+    if (!(cond)) {                       \
+      casmvs::set_error(__VA_ARGS__);    \
+      return -1;                         \
+    }                                    \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ void st4(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+// streaming store: written once, consumed by a later kernel through L2
+__device__ __forceinline__ void st4_stream(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+}  // namespace casmvs

@@ -1,0 +1,181 @@
+// K3 — softmax over the D hypotheses + soft-argmax depth + index + confidence,
+// K4 — depth hypotheses for the next cascade stage.
+//
+// Replaces (reference, relative to /root/reference):
+//   F.softmax + depth_regression    models/mvsnet.py:174-177, models/modules.py:95-104
+//   confidence block                models/mvsnet.py:179-193
+//   get_depth_values                models/modules.py:34-49
+//   x2 bilinear upsample            models/mvsnet.py:231-234
+//   initial uniform planes          models/mvsnet.py:213-229
+#include "common.cuh"
+
+namespace casmvs {
+
+constexpr int kK3Threads = 128;
+
+// Accumulator reproducing torch-CPU's sum over a non-innermost dim for sizes
+// < 256 (ATen SumKernel cascade_sum, level_step 16): 16 terms are added
+// sequentially into acc0, which is then folded into acc1 and cleared; the tail
+// stays in acc0; result = acc0 + acc1.  __fadd_rn keeps ptxas from fusing.
+struct Cascade16 {
+  float a0 = 0.f, a1 = 0.f;
+  int n = 0;
+  __device__ __forceinline__ void add(float t) {
+    a0 = __fadd_rn(a0, t);
+    if (++n == 16) { a1 = __fadd_rn(a1, a0); a0 = 0.f; n = 0; }
+  }
+  __device__ __forceinline__ float result() const { return __fadd_rn(a0, a1); }
+};
+
+template <bool IS_PROB>
+__global__ void __launch_bounds__(kK3Threads)
+regress_kernel(const float* __restrict__ logits, const float* __restrict__ dv, int dv_is_vector,
+               float* __restrict__ depth, float* __restrict__ conf,
+               long long* __restrict__ index, float* __restrict__ prob, int D, int hw) {
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= hw) return;
+  const float* lp = logits + (size_t)b * D * hw + pix;
+  const float* dp = dv_is_vector ? dv : dv + (size_t)b * D * hw + pix;
+  const size_t dstride = dv_is_vector ? 1 : (size_t)hw;
+
+  float m = 0.f, denom = 1.f;
+  if (!IS_PROB) {
+    m = -INFINITY;
+    for (int d = 0; d < D; ++d) m = fmaxf(m, __ldg(lp + (size_t)d * hw));
+    denom = 0.f;
+    for (int d = 0; d < D; ++d) denom = __fadd_rn(denom, expf(__ldg(lp + (size_t)d * hw) - m));
+  }
+  Cascade16 acc_depth, acc_idx;
+  for (int d = 0; d < D; ++d) {
+    float p = __ldg(lp + (size_t)d * hw);
+    if (!IS_PROB) p = __fdiv_rn(expf(p - m), denom);
+    if (prob) prob[(size_t)b * D * hw + (size_t)d * hw + pix] = p;
+    acc_depth.add(__fmul_rn(p, __ldg(dp + d * dstride)));
+    acc_idx.add(__fmul_rn(p, (float)d));
+  }
+  const float dep = acc_depth.result();
+  const float fidx = acc_idx.result();
+  // .long() truncates toward zero; clamp to [0, D-1]  (mvsnet.py:189-190)
+  int idx;
+  if (!(fidx > 0.f)) idx = 0;                       // also catches NaN
+  else if (fidx >= (float)(D - 1)) idx = D - 1;
+  else idx = (int)fidx;
+  // window [idx-1, idx+2], zero padded, summed front to back like avg_pool3d
+  float c = 0.f;
+#pragma unroll
+  for (int k = -1; k <= 2; ++k) {
+    int d = idx + k;
+    float p = 0.f;
+    if (d >= 0 && d < D) {
+      p = __ldg(lp + (size_t)d * hw);
+      if (!IS_PROB) p = __fdiv_rn(expf(p - m), denom);
+    }
+    c = __fadd_rn(c, p);
+  }
+  depth[(size_t)b * hw + pix] = dep;
+  conf[(size_t)b * hw + pix] = c;
+  if (index) index[(size_t)b * hw + pix] = (long long)idx;
+}
+
+// out[b,d,y,x] = max(cur - half_range, 1e-7) + step*d, cur optionally upsampled x2
+// (align_corners=True: src = dst*(in-1)/(out-1)).
+__global__ void __launch_bounds__(256)
+hypotheses_kernel(const float* __restrict__ cur, int upsample, float half_range, float step,
+                  const float* __restrict__ step_dev, float* __restrict__ out, int D, int h,
+                  int w) {
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int hw = h * w;
+  if (pix >= hw) return;
+  float c;
+  if (upsample) {
+    const int hi = h / 2, wi = w / 2;
+    const int y = pix / w, x = pix - y * w;
+    const float sy = hi > 1 ? (float)(hi - 1) / (float)(h - 1) : 0.f;
+    const float sx = wi > 1 ? (float)(wi - 1) / (float)(w - 1) : 0.f;
+    const float fy = sy * (float)y, fx = sx * (float)x;
+    int y0 = (int)fy, x0 = (int)fx;
+    y0 = min(y0, hi - 1); x0 = min(x0, wi - 1);
+    const int y1 = min(y0 + 1, hi - 1), x1 = min(x0 + 1, wi - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const float* cp = cur + (size_t)b * hi * wi;
+    const float v00 = __ldg(cp + y0 * wi + x0), v01 = __ldg(cp + y0 * wi + x1);
+    const float v10 = __ldg(cp + y1 * wi + x0), v11 = __ldg(cp + y1 * wi + x1);
+    const float top = __fadd_rn(__fmul_rn(1.f - lx, v00), __fmul_rn(lx, v01));
+    const float bot = __fadd_rn(__fmul_rn(1.f - lx, v10), __fmul_rn(lx, v11));
+    c = __fadd_rn(__fmul_rn(1.f - ly, top), __fmul_rn(ly, bot));
+  } else {
+    c = __ldg(cur + (size_t)b * hw + pix);
+  }
+  if (step_dev) {
+    step = __ldg(step_dev + b);
+    half_range = __fmul_rn((float)D * 0.5f, step);
+  }
+  const float first = fmaxf(__fsub_rn(c, half_range), 1e-7f);
+  float* op = out + (size_t)b * D * hw + pix;
+  for (int d = 0; d < D; ++d) op[(size_t)d * hw] = __fadd_rn(first, __fmul_rn(step, (float)d));
+}
+
+__global__ void __launch_bounds__(256)
+uniform_hypotheses_kernel(float depth_min, float step, const float* __restrict__ depth_min_dev,
+                          const float* __restrict__ step_dev, float* __restrict__ out, int D,
+                          int hw) {
+  const int b = blockIdx.y;
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= hw) return;
+  if (depth_min_dev) depth_min = __ldg(depth_min_dev + b);
+  if (step_dev) step = __ldg(step_dev + b);
+  float* op = out + (size_t)b * D * hw + pix;
+  for (int d = 0; d < D; ++d) op[(size_t)d * hw] = __fadd_rn(depth_min, __fmul_rn(step, (float)d));
+}
+
+}  // namespace casmvs
+
+using namespace casmvs;
+
+extern "C" int casmvs_regress_fwd(const float* logits, const float* depth_values,
+                                  int dv_is_vector, int input_is_prob, float* depth,
+                                  float* confidence, int64_t* index, float* prob, int B, int D,
+                                  int h, int w, void* stream) {
+  CASMVS_REQUIRE(logits && depth_values && depth && confidence, "regress: null pointer");
+  CASMVS_REQUIRE(B >= 0 && B <= 65535 && D > 0 && h > 0 && w > 0, "regress: bad dims");
+  if (B == 0) return 0;
+  const int hw = h * w;
+  dim3 grd((hw + kK3Threads - 1) / kK3Threads, B);
+  cudaStream_t st = as_stream(stream);
+  if (input_is_prob)
+    regress_kernel<true><<<grd, kK3Threads, 0, st>>>(logits, depth_values, dv_is_vector, depth,
+                                                     confidence, (long long*)index, prob, D, hw);
+  else
+    regress_kernel<false><<<grd, kK3Threads, 0, st>>>(logits, depth_values, dv_is_vector, depth,
+                                                      confidence, (long long*)index, prob, D, hw);
+  return after_launch("regress");
+}
+
+extern "C" int casmvs_depth_hypotheses_fwd(const float* cur, int upsample, float half_range,
+                                           float step, const float* step_dev, float* out, int B,
+                                           int D, int h, int w, void* stream) {
+  CASMVS_REQUIRE(cur && out, "depth_hypotheses: null pointer");
+  CASMVS_REQUIRE(B >= 0 && B <= 65535 && D > 0 && h > 0 && w > 0, "depth_hypotheses: bad dims");
+  CASMVS_REQUIRE(!upsample || (h % 2 == 0 && w % 2 == 0),
+                 "depth_hypotheses: upsample needs even h,w");
+  if (B == 0) return 0;
+  dim3 grd((h * w + 255) / 256, B);
+  hypotheses_kernel<<<grd, 256, 0, as_stream(stream)>>>(cur, upsample, half_range, step, step_dev,
+                                                        out, D, h, w);
+  return after_launch("depth_hypotheses");
+}
+
+extern "C" int casmvs_uniform_hypotheses_fwd(float depth_min, float step,
+                                             const float* depth_min_dev, const float* step_dev,
+                                             float* out, int B, int D, int h, int w,
+                                             void* stream) {
+  CASMVS_REQUIRE(out, "uniform_hypotheses: null pointer");
+  CASMVS_REQUIRE(B >= 0 && B <= 65535 && D > 0 && h > 0 && w > 0, "uniform_hypotheses: bad dims");
+  if (B == 0) return 0;
+  dim3 grd((h * w + 255) / 256, B);
+  uniform_hypotheses_kernel<<<grd, 256, 0, as_stream(stream)>>>(depth_min, step, depth_min_dev,
+                                                                step_dev, out, D, h * w);
+  return after_launch("uniform_hypotheses");
+}

@@ -1,0 +1,200 @@
+"""``CascadeMVSNet`` with the reference's constructor, attributes, state-dict
+keys and forward contract (reference models/mvsnet.py:107-244), running the
+three-stage hot path on the B200 kernels.
+
+Host side (this file) is glue: it owns the parameters, runs the 2D FeatureNet
+with PyTorch/cuDNN in channels-last (so the fused warp kernel gets HWC features
+without a transpose) and sequences K4 -> K1 -> K2 -> K3 per stage.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..norm_act import activation_slope, folded_scale_shift
+from .modules import *  # noqa: F401,F403  (reference does the same, mvsnet.py:5)
+from .modules import ConvBnReLU, ConvBnReLU3D, InPlaceABN
+
+
+class FeatureNet(nn.Module):
+    """3-level FPN (reference models/mvsnet.py:7-57).  PyTorch/cuDNN."""
+
+    def __init__(self, norm_act=InPlaceABN):
+        super().__init__()
+        self.conv0 = nn.Sequential(ConvBnReLU(3, 8, 3, 1, 1, norm_act=norm_act),
+                                   ConvBnReLU(8, 8, 3, 1, 1, norm_act=norm_act))
+        self.conv1 = nn.Sequential(ConvBnReLU(8, 16, 5, 2, 2, norm_act=norm_act),
+                                   ConvBnReLU(16, 16, 3, 1, 1, norm_act=norm_act),
+                                   ConvBnReLU(16, 16, 3, 1, 1, norm_act=norm_act))
+        self.conv2 = nn.Sequential(ConvBnReLU(16, 32, 5, 2, 2, norm_act=norm_act),
+                                   ConvBnReLU(32, 32, 3, 1, 1, norm_act=norm_act),
+                                   ConvBnReLU(32, 32, 3, 1, 1, norm_act=norm_act))
+        self.toplayer = nn.Conv2d(32, 32, 1)
+        self.lat1 = nn.Conv2d(16, 32, 1)
+        self.lat0 = nn.Conv2d(8, 32, 1)
+        self.smooth1 = nn.Conv2d(32, 16, 3, padding=1)
+        self.smooth0 = nn.Conv2d(32, 8, 3, padding=1)
+
+    @staticmethod
+    def _up2(x):
+        return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
+
+    def forward(self, x):
+        # channels-last end to end: level_l come out physically (N,h,w,C)
+        x = x.contiguous(memory_format=torch.channels_last)
+        c0 = self.conv0(x)
+        c1 = self.conv1(c0)
+        c2 = self.conv2(c1)
+        f2 = self.toplayer(c2)
+        f1 = self._up2(f2) + self.lat1(c1)
+        f0 = self._up2(f1) + self.lat0(c0)
+        f1 = self.smooth1(f1)
+        f0 = self.smooth0(f0)
+        return {"level_0": f0.contiguous(memory_format=torch.channels_last),
+                "level_1": f1.contiguous(memory_format=torch.channels_last),
+                "level_2": f2.contiguous(memory_format=torch.channels_last)}
+
+
+class CostRegNet(nn.Module):
+    """3D U-Net cost regularisation (reference models/mvsnet.py:60-104).
+
+    Sub-module names/shapes follow the reference so checkpoints load unchanged;
+    ``forward`` hands the whole 11-layer stack to ``casmvs_costreg_fwd``."""
+
+    _ORDER = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6",
+              "conv7", "conv9", "conv11", "prob")
+
+    def __init__(self, in_channels, norm_act=InPlaceABN):
+        super().__init__()
+        self.in_channels = in_channels
+        self.conv0 = ConvBnReLU3D(in_channels, 8, norm_act=norm_act)
+        self.conv1 = ConvBnReLU3D(8, 16, stride=2, norm_act=norm_act)
+        self.conv2 = ConvBnReLU3D(16, 16, norm_act=norm_act)
+        self.conv3 = ConvBnReLU3D(16, 32, stride=2, norm_act=norm_act)
+        self.conv4 = ConvBnReLU3D(32, 32, norm_act=norm_act)
+        self.conv5 = ConvBnReLU3D(32, 64, stride=2, norm_act=norm_act)
+        self.conv6 = ConvBnReLU3D(64, 64, norm_act=norm_act)
+
+        def up(cin, cout):
+            return nn.Sequential(nn.ConvTranspose3d(cin, cout, 3, padding=1, output_padding=1,
+                                                    stride=2, bias=False), norm_act(cout))
+        self.conv7 = up(64, 32)
+        self.conv9 = up(32, 16)
+        self.conv11 = up(16, 8)
+        self.prob = nn.Conv3d(8, 1, 3, stride=1, padding=1)
+        self.precision = "fp32"
+        self._blob = None
+        self._blob_key = None
+
+    def _layer_tensors(self, name):
+        m = getattr(self, name)
+        if name == "prob":
+            return m.weight, None, m.bias
+        if isinstance(m, ConvBnReLU3D):
+            return m.conv.weight, m.bn, None
+        return m[0].weight, m[1], None
+
+    def _norm_modules(self):
+        for name in self._ORDER[:-1]:
+            yield self._layer_tensors(name)[1]
+
+    def packed_params(self):
+        """Device blob for casmvs_costreg_fwd (layout: casmvs_costreg_layer_info)."""
+        key = tuple((t.data_ptr(), t._version) for t in
+                    list(self.parameters()) + list(self.buffers()))
+        if key == self._blob_key:
+            return self._blob
+        dev = self.prob.weight.device
+        n = ops._lib.load().casmvs_costreg_param_floats(self.in_channels)
+        blob = torch.empty(n, device=dev, dtype=torch.float32)
+        for i, name in enumerate(self._ORDER):
+            info = ops.costreg_layer_info(self.in_channels, i)
+            w, bn, bias = self._layer_tensors(name)
+            wp = ops.pack_conv3d_weight(w, info["kind"])
+            blob[info["w_off"]:info["w_off"] + wp.numel()] = wp
+            co = info["cout"]
+            if bn is not None:
+                a, b = folded_scale_shift(bn)
+            else:
+                a = torch.ones(co, device=dev)
+                b = bias.detach().float()
+            blob[info["scale_off"]:info["scale_off"] + co] = a
+            blob[info["shift_off"]:info["shift_off"] + co] = b
+        self._blob, self._blob_key = blob, key
+        return blob
+
+    def forward(self, x):
+        for bn in self._norm_modules():
+            if bn.training:
+                raise ops._lib.CasMVSError("CostRegNet is inference-only: call .eval() first")
+            if abs(activation_slope(bn) - 0.01) > 1e-12:
+                raise ops._lib.CasMVSError("casmvs_costreg_fwd assumes LeakyReLU(0.01) norm_act")
+        logits = ops.costreg(x, self.packed_params(), self.in_channels,
+                             ops.PRECISIONS[self.precision])
+        return logits.unsqueeze(1)                                   # (B,1,D,h,w)
+
+
+class CascadeMVSNet(nn.Module):
+    def __init__(self, n_depths=[8, 32, 48], interval_ratios=[1, 2, 4], num_groups=1,
+                 norm_act=InPlaceABN, precision="fp32"):
+        super().__init__()
+        self.levels = 3
+        self.n_depths = n_depths
+        self.interval_ratios = interval_ratios
+        self.G = num_groups
+        self.feature = FeatureNet(norm_act)
+        for l in range(self.levels):
+            cin = self.G if self.G > 1 else 8 * 2 ** l
+            setattr(self, f"cost_reg_{l}", CostRegNet(cin, norm_act))
+        self.set_precision(precision)
+
+    def set_precision(self, precision):
+        """'fp32' (CUDA-core FMA), 'tf32' (tcgen05) or 'tf32x3' for the 3D convs."""
+        if precision not in ops.PRECISIONS:
+            raise ValueError(f"precision must be one of {list(ops.PRECISIONS)}")
+        self.precision = precision
+        for m in self.modules():
+            if isinstance(m, (CostRegNet, ConvBnReLU3D)):
+                m.precision = precision
+        return self
+
+    def predict_depth(self, feats, proj_mats, depth_values, cost_reg):
+        """feats (B,V,C,h,w), proj_mats (B,V-1,3,4), depth_values (B,D,h,w),
+        cost_reg: module (B,C,D,h,w)->(B,1,D,h,w).  Returns depth, confidence (B,h,w)
+        (reference models/mvsnet.py:125-195)."""
+        cost = ops.warp_cost(feats, proj_mats, depth_values, self.G, ops.NHWC)
+        logits = cost_reg(cost).squeeze(1)
+        del cost
+        depth, confidence, _, _ = ops.regress(logits, depth_values)
+        return depth, confidence
+
+    def forward(self, imgs, proj_mats, init_depth_min, depth_interval):
+        """imgs (B,V,3,H,W); proj_mats (B,V-1,levels,3,4) fine->coarse;
+        init_depth_min, depth_interval: float or (B,1) tensors.
+        Returns {depth_l, confidence_l : (B,h_l,w_l)} (reference mvsnet.py:197-244)."""
+        B, V, _, H, W = imgs.shape
+        if not imgs.is_cuda:
+            raise ops._lib.CasMVSError(
+                "CascadeMVSNet (B200 engine) needs CUDA inputs; there is no CPU fallback")
+        results = {}
+        with torch.no_grad():
+            feats = self.feature(imgs.reshape(B * V, 3, H, W))
+            depth_l = None
+            for l in reversed(range(self.levels)):
+                feats_l = feats[f"level_{l}"]
+                feats_l = feats_l.view(B, V, *feats_l.shape[1:])
+                proj_mats_l = proj_mats[:, :, l]
+                depth_interval_l = depth_interval * self.interval_ratios[l]
+                D = self.n_depths[l]
+                h, w = feats_l.shape[-2:]
+                if l == self.levels - 1:
+                    depth_values = ops.uniform_hypotheses(init_depth_min, depth_interval_l, D,
+                                                          B, h, w, imgs.device)
+                else:
+                    depth_values = ops.depth_hypotheses(depth_l, D, depth_interval_l,
+                                                        upsample=True)
+                depth_l, confidence_l = self.predict_depth(
+                    feats_l, proj_mats_l, depth_values, getattr(self, f"cost_reg_{l}"))
+                results[f"depth_{l}"] = depth_l
+                results[f"confidence_{l}"] = confidence_l
+        return results

@@ -1,0 +1,253 @@
+"""torch-tensor wrappers over the C ABI (include/casmvs.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every op below
+is a call into libcasmvs.so.  CPU tensors are rejected — there is no fallback
+(`eval.py --cpu` stays an oracle-only mode).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import CONV, CONV_TRANSPOSE, FP32, NCHW, NHWC, PRECISIONS, check
+
+_checked_devices = set()
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.CasMVSError(
+                "casmvsnet_pl_b200 ops need CUDA tensors on a B200 (no CPU fallback); "
+                f"got a tensor on {t.device}")
+        if t.dtype != torch.float32:
+            raise _lib.CasMVSError(f"fp32 only (reference opt.py:69-70), got {t.dtype}")
+    dev = tensors[0].device.index
+    if dev is None:
+        dev = torch.cuda.current_device()
+    if dev not in _checked_devices:
+        check(_lib.load().casmvs_device_check(dev), "device_check")
+        _checked_devices.add(dev)
+
+
+def _no_grad_only(*tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise _lib.CasMVSError(
+            "the B200 engine is forward-only this round (SURVEY.md §8f-1): call it under "
+            "torch.no_grad() or with tensors that do not require grad")
+
+
+def is_channels_last_feats(feats):
+    """feats (..., C, h, w): True if physically (..., h, w, C) dense."""
+    C, h, w = feats.shape[-3:]
+    st = feats.stride()
+    if not (st[-3] == 1 and st[-1] == C and st[-2] == w * C):
+        return False
+    expect = h * w * C
+    for size, s in zip(reversed(feats.shape[:-3]), reversed(st[:-3])):
+        if size != 1 and s != expect:
+            return False
+        expect *= size
+    return True
+
+
+def as_volume_view(buf_ndhwc):
+    """(B,D,h,w,C) buffer -> logical (B,C,D,h,w) view (channels_last_3d strides)."""
+    return buf_ndhwc.permute(0, 4, 1, 2, 3)
+
+
+def volume_storage(x):
+    """logical (B,C,D,h,w) -> dense (B,D,h,w,C) storage (copy only if needed)."""
+    v = x.permute(0, 2, 3, 4, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+# --------------------------------------------------------------------------- K1
+def warp_cost(feats, proj_mats, depth_values, num_groups=1, out_layout=NHWC):
+    """Fused homography warp + variance / group-wise-correlation cost volume.
+
+    feats (B,V,C,h,w) (any strides; channels-last storage is used as is),
+    proj_mats (B,V-1,3,4), depth_values (B,D,h,w).
+    Returns the LOGICAL (B,Cout,D,h,w) tensor; with out_layout=NHWC its memory
+    is (B,D,h,w,Cout) (torch channels_last_3d), what the conv stack consumes.
+    """
+    _require_cuda(feats, proj_mats, depth_values)
+    _no_grad_only(feats)
+    B, V, C, h, w = feats.shape
+    D = depth_values.shape[1]
+    lib = _lib.load()
+    if is_channels_last_feats(feats):
+        flayout, fbuf = NHWC, feats
+    else:
+        flayout, fbuf = NCHW, feats.contiguous()
+    proj = proj_mats.contiguous()
+    dv = depth_values.contiguous()
+    assert proj.shape == (B, V - 1, 3, 4) and dv.shape == (B, D, h, w)
+    cout = C if num_groups == 1 else num_groups
+    ws_bytes = lib.casmvs_warp_cost_workspace_bytes(flayout, B, V, C, h, w)
+    ws = torch.empty(ws_bytes // 4, device=feats.device, dtype=torch.float32) if ws_bytes else None
+    if out_layout == NHWC:
+        out = torch.empty(B, D, h, w, cout, device=feats.device, dtype=torch.float32)
+    else:
+        out = torch.empty(B, cout, D, h, w, device=feats.device, dtype=torch.float32)
+    check(lib.casmvs_warp_cost_fwd(_ptr(fbuf), flayout, _ptr(proj), _ptr(dv), _ptr(out),
+                                   out_layout, B, V, C, D, h, w, num_groups, _ptr(ws),
+                                   ws_bytes, _stream()), "warp_cost")
+    return as_volume_view(out) if out_layout == NHWC else out
+
+
+def homo_warp(src_feat, proj_mat, depth_values):
+    """models/modules.py:52-92.  src_feat (B,C,h,w), proj_mat (B,3,4),
+    depth_values (B,D,h,w) -> (B,C,D,h,w) contiguous (reference layout)."""
+    _require_cuda(src_feat, proj_mat, depth_values)
+    _no_grad_only(src_feat)
+    B, C, h, w = src_feat.shape
+    D = depth_values.shape[1]
+    lib = _lib.load()
+    if is_channels_last_feats(src_feat):
+        fbuf = src_feat
+    else:
+        fbuf = torch.empty(B, h, w, C, device=src_feat.device, dtype=torch.float32)
+        check(lib.casmvs_nchw_to_nhwc(_ptr(src_feat.contiguous()), _ptr(fbuf), B, C, h * w,
+                                      _stream()), "nchw_to_nhwc")
+    out = torch.empty(B, C, D, h, w, device=src_feat.device, dtype=torch.float32)
+    check(lib.casmvs_homo_warp_fwd(_ptr(fbuf), NHWC, _ptr(proj_mat.contiguous()),
+                                   _ptr(depth_values.contiguous()), _ptr(out), NCHW,
+                                   B, C, D, h, w, _stream()), "homo_warp")
+    return out
+
+
+# --------------------------------------------------------------------------- K2
+def pack_conv3d_weight(weight, kind):
+    """torch Conv3d (Cout,Cin,3,3,3) / ConvTranspose3d (Cin,Cout,3,3,3) -> [27][Cin][Cout]."""
+    _require_cuda(weight)
+    if kind == CONV:
+        cout, cin = weight.shape[:2]
+    else:
+        cin, cout = weight.shape[:2]
+    out = torch.empty(27 * cin * cout, device=weight.device, dtype=torch.float32)
+    check(_lib.load().casmvs_pack_conv3d_weights(_ptr(weight.detach().contiguous()), kind, cin,
+                                                 cout, _ptr(out), _stream()), "pack_conv3d")
+    return out
+
+
+def conv3d(x, w_packed, cin, cout, scale=None, shift=None, slope=1.0, skip=None,
+           kind=CONV, stride=1, precision=FP32):
+    """x logical (B,Cin,D,h,w) -> logical (B,Cout,Do,ho,wo); storage channels-last."""
+    _require_cuda(x, w_packed, scale, shift, skip)
+    _no_grad_only(x)
+    xs = volume_storage(x)
+    B, D, h, w, _ = xs.shape
+    if kind == CONV:
+        Do, ho, wo = (D - 1) // stride + 1, (h - 1) // stride + 1, (w - 1) // stride + 1
+    else:
+        Do, ho, wo = 2 * D, 2 * h, 2 * w
+    y = torch.empty(B, Do, ho, wo, cout, device=x.device, dtype=torch.float32)
+    sk = volume_storage(skip) if skip is not None else None
+    check(_lib.load().casmvs_conv3d_fwd(_ptr(xs), _ptr(w_packed), _ptr(scale), _ptr(shift),
+                                        float(slope), _ptr(sk), _ptr(y), B, cin, cout, D, h, w,
+                                        kind, stride, precision, _stream()), "conv3d")
+    return as_volume_view(y)
+
+
+def costreg_layer_info(cin, layer):
+    lib = _lib.load()
+    ci, co, kind, stride = (ctypes.c_int() for _ in range(4))
+    wo, so, ho = (ctypes.c_size_t() for _ in range(3))
+    check(lib.casmvs_costreg_layer_info(cin, layer, ci, co, kind, stride, wo, so, ho),
+          "costreg_layer_info")
+    return dict(cin=ci.value, cout=co.value, kind=kind.value, stride=stride.value,
+                w_off=wo.value, scale_off=so.value, shift_off=ho.value)
+
+
+def costreg(x, params, cin, precision=FP32):
+    """Whole CostRegNet.  x logical (B,Cin,D,h,w) -> logits (B,D,h,w)."""
+    _require_cuda(x, params)
+    _no_grad_only(x)
+    xs = volume_storage(x)
+    B, D, h, w, c = xs.shape
+    assert c == cin
+    lib = _lib.load()
+    ws_bytes = lib.casmvs_costreg_workspace_bytes(B, cin, D, h, w)
+    ws = torch.empty(ws_bytes // 4, device=x.device, dtype=torch.float32)
+    logits = torch.empty(B, D, h, w, device=x.device, dtype=torch.float32)
+    check(lib.casmvs_costreg_fwd(_ptr(xs), _ptr(params), _ptr(logits), B, cin, D, h, w,
+                                 precision, _ptr(ws), ws_bytes, _stream()), "costreg")
+    return logits
+
+
+# --------------------------------------------------------------------------- K3
+def regress(logits, depth_values, input_is_prob=False, want_index=False, want_prob=False):
+    """softmax + soft-argmax depth + confidence (+ index, prob).
+    logits (B,D,h,w); depth_values (B,D,h,w) or (D,)."""
+    _require_cuda(logits, depth_values)
+    _no_grad_only(logits)
+    lg = logits.contiguous()
+    B, D, h, w = lg.shape
+    dv_vec = depth_values.dim() == 1
+    dv = depth_values.contiguous()
+    depth = torch.empty(B, h, w, device=lg.device, dtype=torch.float32)
+    conf = torch.empty_like(depth)
+    index = torch.empty(B, h, w, device=lg.device, dtype=torch.int64) if want_index else None
+    prob = torch.empty_like(lg) if want_prob else None
+    check(_lib.load().casmvs_regress_fwd(_ptr(lg), _ptr(dv), int(dv_vec), int(input_is_prob),
+                                         _ptr(depth), _ptr(conf), _ptr(index), _ptr(prob),
+                                         B, D, h, w, _stream()), "regress")
+    return depth, conf, index, prob
+
+
+# --------------------------------------------------------------------------- K4
+def _interval_args(depth_interval, B, device):
+    """float -> (scalar, None); tensor (B,1)/(B,) -> (0.0, device (B,) tensor)."""
+    if isinstance(depth_interval, (float, int)):
+        return float(depth_interval), None
+    t = depth_interval.reshape(-1).to(device=device, dtype=torch.float32).contiguous()
+    if t.numel() == 1 and B > 1:
+        t = t.expand(B).contiguous()
+    assert t.numel() == B
+    return 0.0, t
+
+
+def depth_hypotheses(current_depth, n_depths, depth_interval, upsample=False):
+    """get_depth_values (models/modules.py:34-49), optionally fused with the x2
+    bilinear upsample of models/mvsnet.py:231-234.
+    current_depth (B,1,h,w), or (B,h/2,w/2) when upsample=True -> (B,D,h,w)."""
+    _require_cuda(current_depth)
+    cur = current_depth.contiguous()
+    if upsample:
+        B, hi, wi = cur.shape
+        h, w = 2 * hi, 2 * wi
+    else:
+        B, _, h, w = cur.shape
+    step, step_dev = _interval_args(depth_interval, B, cur.device)
+    # python-float interval: the reference forms n/2*interval in double, torch
+    # then rounds the scalar to fp32 for the tensor op (modules.py:44)
+    half = float(n_depths / 2 * step)
+    out = torch.empty(B, n_depths, h, w, device=cur.device, dtype=torch.float32)
+    check(_lib.load().casmvs_depth_hypotheses_fwd(_ptr(cur), int(upsample), half, step,
+                                                  _ptr(step_dev), _ptr(out), B, n_depths, h, w,
+                                                  _stream()), "depth_hypotheses")
+    return out
+
+
+def uniform_hypotheses(init_depth_min, depth_interval, n_depths, B, h, w, device):
+    """models/mvsnet.py:213-229 -> (B,D,h,w)."""
+    dmin, dmin_dev = _interval_args(init_depth_min, B, device)
+    step, step_dev = _interval_args(depth_interval, B, device)
+    out = torch.empty(B, n_depths, h, w, device=device, dtype=torch.float32)
+    check(_lib.load().casmvs_uniform_hypotheses_fwd(dmin, step, _ptr(dmin_dev), _ptr(step_dev),
+                                                    _ptr(out), B, n_depths, h, w, _stream()),
+          "uniform_hypotheses")
+    return out

@@ -1,0 +1,163 @@
+/*
+ * casmvs.h — C ABI of libcasmvs.so, the B200 (sm_100a) cascade-MVS depth engine.
+ *
+ * The reference (kwea123/CasMVSNet_pl) has NO FFI layer: its boundary for the
+ * hot path is the Python surface models/mvsnet.py + models/modules.py
+ * (SURVEY.md §8b).  This header is the C boundary a binding for that surface
+ * needs; each entry cites the reference code it replaces (paths relative to
+ * the reference root).  The Python binding that mirrors the reference API on
+ * top of it lives in casmvsnet_pl_b200/models/ and is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; casmvs_last_error()
+ *    returns a thread-local description.  No exceptions cross the boundary.
+ *  - all tensor arguments are raw DEVICE pointers owned by the caller (e.g.
+ *    torch.Tensor.data_ptr()); the library never allocates or frees
+ *    user-visible memory.  Scratch memory is passed in as workspace.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *    the call returns without synchronising (CUDA-graph capturable).
+ *  - fp32 everywhere (the reference declares AMP unsupported, opt.py:69-70);
+ *    depth_index is int64 like torch's .long().
+ *  - there is no CPU fallback: casmvs_device_check() fails on anything below
+ *    compute capability 10.0.
+ *
+ * Memory layouts (enum casmvs_layout)
+ *   CASMVS_NCHW : channels-first, the reference's public layout
+ *                 features (B,V,C,h,w), volumes (B,C,D,h,w)
+ *   CASMVS_NHWC : channels-last, the engine's internal layout
+ *                 features (B,V,h,w,C), volumes (B,D,h,w,C)
+ */
+#ifndef CASMVS_H_
+#define CASMVS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CASMVS_VERSION 100  /* 0.1.0 */
+
+enum casmvs_layout { CASMVS_NCHW = 0, CASMVS_NHWC = 1 };
+
+/* precision of the 3D-conv contraction (K2) */
+enum casmvs_precision {
+  CASMVS_FP32 = 0,  /* CUDA-core fp32 FMA (bit-faithful products)            */
+  CASMVS_TF32 = 1,  /* tcgen05 kind::tf32, fp32 accumulate in TMEM           */
+  CASMVS_TF32X3 = 2 /* error-compensated 3xTF32 split (fp32-equivalent)      */
+};
+
+enum casmvs_conv_kind {
+  CASMVS_CONV = 0,          /* Conv3d(k=3, pad=1, stride 1|2)   modules.py:26      */
+  CASMVS_CONV_TRANSPOSE = 1 /* ConvTranspose3d(k=3,s=2,p=1,op=1) mvsnet.py:75,80,85 */
+};
+
+/* ---- library / device ------------------------------------------------- */
+int casmvs_version(void);
+const char* casmvs_last_error(void);
+/* 0 iff `device` exists and has compute capability >= 10.0 (no fallback). */
+int casmvs_device_check(int device);
+/* number of kernels this library has launched since load (bench evidence). */
+uint64_t casmvs_launch_count(void);
+
+/* ---- K1: fused homography warp + bilinear sample + cost reduction ------
+ * Replaces homo_warp (models/modules.py:52-92) called V-1 times plus the
+ * variance (models/mvsnet.py:137-141,147-156,166-168) or group-wise
+ * correlation (:143-144,158-162,170-172) accumulation.  The warped
+ * (B,V-1,C,D,h,w) volumes are never materialised.
+ *   feats        (B,V,C,h,w) [NCHW] or (B,V,h,w,C) [NHWC]; view 0 = reference
+ *   proj         (B,V-1,3,4) row-major  src_proj @ ref_proj^-1
+ *   depth_values (B,D,h,w)
+ *   cost         num_groups==1: C channels  (B,C,D,h,w)|(B,D,h,w,C)
+ *                num_groups >1: G channels  (B,G,D,h,w)|(B,D,h,w,G)
+ * Workspace: casmvs_warp_cost_workspace_bytes() (only needed when feats are
+ * NCHW: they are re-laid-out once to NHWC).  C % 8 == 0, C % G == 0.
+ */
+size_t casmvs_warp_cost_workspace_bytes(int feat_layout, int B, int V, int C, int h, int w);
+int casmvs_warp_cost_fwd(const float* feats, int feat_layout, const float* proj,
+                         const float* depth_values, float* cost, int cost_layout,
+                         int B, int V, int C, int D, int h, int w, int num_groups,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stand-alone homo_warp (models/modules.py:52-92): materialises the warped
+ * volume for API completeness.  src_feat (B,C,h,w)|(B,h,w,C), proj (B,3,4),
+ * depth_values (B,D,h,w) -> warped (B,C,D,h,w)|(B,D,h,w,C).               */
+int casmvs_homo_warp_fwd(const float* src_feat, int feat_layout, const float* proj,
+                         const float* depth_values, float* warped, int out_layout,
+                         int B, int C, int D, int h, int w, void* stream);
+
+/* ---- K2: 3x3x3 convolution with fused norm-act epilogue ----------------
+ * Replaces ConvBnReLU3D (models/modules.py:21-31), the ConvTranspose3d +
+ * norm_act pairs and the skip additions of CostRegNet.forward
+ * (models/mvsnet.py:60-104) and its `prob` head (:89,103).
+ *   y = act( conv(x, w) * scale[c] + shift[c] ) + skip
+ *   act(v) = v >= 0 ? v : slope * v   (slope = 1 -> identity, used by `prob`)
+ * Volumes are channels-last (B,D,h,w,C).  Weights are pre-packed with
+ * casmvs_pack_conv3d_weights (tap-major [27][Cin][Cout]).
+ * For kind == CASMVS_CONV: stride in {1,2}, out dims = (in-1)/stride+1.
+ * For kind == CASMVS_CONV_TRANSPOSE: out dims = 2*in.
+ */
+size_t casmvs_packed_conv3d_weight_floats(int Cin, int Cout);
+/* w_torch: Conv3d layout (Cout,Cin,3,3,3) or ConvTranspose3d layout (Cin,Cout,3,3,3) */
+int casmvs_pack_conv3d_weights(const float* w_torch, int kind, int Cin, int Cout,
+                               float* w_packed, void* stream);
+int casmvs_conv3d_fwd(const float* x, const float* w_packed, const float* scale,
+                      const float* shift, float slope, const float* skip, float* y,
+                      int B, int Cin, int Cout, int D, int h, int w, /* INPUT dims */
+                      int kind, int stride, int precision, void* stream);
+
+/* Whole CostRegNet (models/mvsnet.py:91-104) in one call.  `params` is a
+ * device array produced by casmvs_costreg_pack (see casmvs_costreg_param_floats).
+ * x (B,D,h,w,Cin) -> logits (B,D,h,w) ; D,h,w divisible by 8.                */
+size_t casmvs_costreg_param_floats(int Cin);
+/* Layout of the params blob: layers 0..10 = conv0..conv6, conv7, conv9, conv11,
+ * prob; each is packed weights [27][cin][cout], scale[cout], shift[cout]
+ * (scale/shift = folded eval-mode ABN: alpha = gamma/sqrt(var+eps),
+ * beta' = beta - mean*alpha; prob: scale = 1, shift = bias).  Offsets in floats. */
+int casmvs_costreg_layer_info(int Cin, int layer, int* cin, int* cout, int* kind, int* stride,
+                              size_t* w_off, size_t* scale_off, size_t* shift_off);
+size_t casmvs_costreg_workspace_bytes(int B, int Cin, int D, int h, int w);
+int casmvs_costreg_fwd(const float* x, const float* params, float* logits,
+                       int B, int Cin, int D, int h, int w, int precision,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K3: softmax over D + depth regression + index + confidence --------
+ * Replaces F.softmax + depth_regression (models/mvsnet.py:174-177,
+ * models/modules.py:95-104) and the confidence block (:179-193).
+ *   logits (B,D,h,w); depth_values (B,D,h,w) or, if dv_is_vector, (D,)
+ *   depth (B,h,w) f32, confidence (B,h,w) f32,
+ *   index (B,h,w) int64 or NULL, prob (B,D,h,w) or NULL.
+ * input_is_prob != 0 skips the softmax (logits already hold probabilities).
+ * Sums over D use torch-CPU's order (16-term chunks cascaded) so that
+ * depth_index is bit-exact against the oracle for identical p.            */
+int casmvs_regress_fwd(const float* logits, const float* depth_values, int dv_is_vector,
+                       int input_is_prob, float* depth, float* confidence,
+                       int64_t* index, float* prob, int B, int D, int h, int w,
+                       void* stream);
+
+/* ---- K4: depth hypotheses ----------------------------------------------
+ * casmvs_depth_hypotheses_fwd replaces get_depth_values
+ * (models/modules.py:34-49): out[b,d] = max(cur - half_range, 1e-7) + step*d.
+ * If upsample != 0 `cur` is (B,h/2,w/2) and is first upsampled x2 bilinear,
+ * align_corners=True (models/mvsnet.py:231-234); else `cur` is (B,h,w).
+ * step_dev (B floats, device) overrides `step`/`half_range` when non-NULL
+ * (tensor-valued depth_interval): half_range = fl32(D/2)*step_dev[b].
+ * casmvs_uniform_hypotheses_fwd replaces models/mvsnet.py:213-229:
+ * out[b,d,:,:] = depth_min + step*d, depth_min/step scalars or device (B,).  */
+int casmvs_depth_hypotheses_fwd(const float* cur, int upsample, float half_range,
+                                float step, const float* step_dev, float* out,
+                                int B, int D, int h, int w, void* stream);
+int casmvs_uniform_hypotheses_fwd(float depth_min, float step, const float* depth_min_dev,
+                                  const float* step_dev, float* out,
+                                  int B, int D, int h, int w, void* stream);
+
+/* ---- layout helpers ------------------------------------------------------ */
+/* (N,C,S) -> (N,S,C) and back, S = product of spatial dims. */
+int casmvs_nchw_to_nhwc(const float* in, float* out, int N, int C, size_t S, void* stream);
+int casmvs_nhwc_to_nchw(const float* in, float* out, int N, int C, size_t S, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CASMVS_H_ */

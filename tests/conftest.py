@@ -1,0 +1,24 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    import torch
+
+    def load(name):
+        path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+        with np.load(path) as z:
+            return {k: torch.from_numpy(z[k]) for k in z.files}
+    return load

@@ -1,0 +1,269 @@
+"""GPU parity tests proper: every kernel, called through the C ABI (ops.py ->
+libcasmvs.so), against the golden vectors of the real reference and against the
+CPU oracle on seeded inputs.  Tolerances are stated next to each assert.
+
+Sampling-position note (K1): the kernel evaluates u = q_x/q_z directly; the
+reference normalises to [-1,1] and grid_sample un-normalises (modules.py:83-89).
+Both are fp32, so sample positions differ by a few ulp(u) (ulp(600 px) = 6e-5)
+and a warped value by that times the local feature gradient.  Tolerances below
+are expressed on that basis and the fp64 test shows the kernel is at least as
+close to exact arithmetic as the reference is.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from casmvsnet_pl_b200 import _lib, ops, synth           # noqa: E402
+from oracle import casmvs_oracle as O                    # noqa: E402
+
+DEV = "cuda:0"
+
+
+def cl(feats):
+    """(B,V,C,h,w) -> same logical tensor, channels-last storage."""
+    return feats.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+
+
+def stats(name, got, ref):
+    err = (got - ref).abs()
+    print(f"{name}: max|err|={err.max().item():.3e} mean|err|={err.mean().item():.3e} "
+          f"max|ref|={ref.abs().max().item():.3e}")
+    return err
+
+
+# ----------------------------------------------------------------------------- K1
+def test_homo_warp_vs_reference_golden(golden):
+    g = golden("homo_warp")
+    out = ops.homo_warp(g["feat"].to(DEV), g["proj"].to(DEV), g["depth_values"].to(DEV)).cpu()
+    err = stats("homo_warp", out, g["warped"])
+    # w=40: ulp(u) <= 4e-6, |grad| of N(0,1) texels ~ few units -> 5e-5 absolute
+    assert err.max() < 5e-5
+    # exact zeros where the reference has them (behind camera / out of bounds)
+    assert torch.equal(out == 0, g["warped"] == 0)
+
+
+@pytest.mark.parametrize("tag", ["var_c8", "var_c32_v5", "gwc_c16_g8", "gwc_c32_g8", "gwc_c32_g2"])
+@pytest.mark.parametrize("layout", ["nchw_in_nchw_out", "nhwc_in_nhwc_out"])
+def test_cost_volume_vs_reference_golden(golden, tag, layout):
+    g = golden("cost_" + tag)
+    G = int(g["G"])
+    feats = g["feats"].to(DEV)
+    if layout.startswith("nhwc"):
+        feats = cl(feats)
+    out_layout = ops.NHWC if layout.endswith("nhwc_out") else ops.NCHW
+    out = ops.warp_cost(feats, g["proj"].to(DEV), g["depth_values"].to(DEV), G, out_layout)
+    assert out.shape == g["cost"].shape
+    err = stats(f"cost_{tag}/{layout}", out.cpu(), g["cost"])
+    # variance of O(1) features: values up to ~10; sampling ulps + reciprocal-multiply
+    # instead of /V (1 ulp each) -> 1e-4 absolute, 2e-5 relative to max
+    assert err.max() < 1e-4
+    assert err.max() / g["cost"].abs().max() < 2e-5
+
+
+def test_cost_volume_no_less_accurate_than_reference_fp64():
+    """Both fp32 implementations against an fp64 evaluation of the same formula."""
+    g = torch.Generator().manual_seed(4)
+    B, V, C, h, w, D = 1, 3, 16, 64, 80, 16
+    feats = torch.randn(B, V, C, h, w, generator=g)
+    pm = synth.projection_matrices(V, W=4 * w, H=4 * h, stress=True)[:, 2].unsqueeze(0)
+    dv = 450.0 + 10.6 * torch.arange(D).float().reshape(1, D, 1, 1) + torch.rand(B, D, h, w, generator=g)
+    ref32 = O.variance_cost_volume(feats, pm, dv)
+    # fp64: direct bilinear, double arithmetic
+    f64 = feats.double()
+    S = f64[:, 0].unsqueeze(2).expand(-1, -1, D, -1, -1).clone()
+    Q = S ** 2
+    for v in range(1, V):
+        wv = _warp_fp64(f64[:, v], pm[:, v - 1].double(), dv.double())
+        S = S + wv
+        Q = Q + wv ** 2
+    ref64 = Q / V - (S / V) ** 2
+    got = ops.warp_cost(feats.to(DEV), pm.to(DEV), dv.to(DEV), 1, ops.NCHW).cpu()
+    e_ref = (ref32.double() - ref64).abs()
+    e_got = (got.double() - ref64).abs()
+    print(f"vs fp64: reference-fp32 max {e_ref.max():.3e} mean {e_ref.mean():.3e}; "
+          f"kernel max {e_got.max():.3e} mean {e_got.mean():.3e}")
+    assert e_got.mean() <= 1.5 * e_ref.mean() + 1e-9
+    assert e_got.max() <= 3.0 * e_ref.max() + 1e-7
+
+
+def _warp_fp64(src, P, dv):
+    B, C, h, w = src.shape
+    D = dv.shape[1]
+    ys, xs = torch.meshgrid(torch.arange(h, dtype=torch.float64),
+                            torch.arange(w, dtype=torch.float64), indexing="ij")
+    out = torch.zeros(B, C, D, h, w, dtype=torch.float64)
+    for b in range(B):
+        p = P[b]
+        qx = p[0, 0] * xs + p[0, 1] * ys + p[0, 2] + p[0, 3] / dv[b]
+        qy = p[1, 0] * xs + p[1, 1] * ys + p[1, 2] + p[1, 3] / dv[b]
+        qz = p[2, 0] * xs + p[2, 1] * ys + p[2, 2] + p[2, 3] / dv[b]
+        u, v = qx / qz, qy / qz
+        bad = qz <= 1e-7
+        u[bad], v[bad] = w, h
+        x0, y0 = torch.floor(u), torch.floor(v)
+        fx, fy = u - x0, v - y0
+        for dy, dx, wt in ((0, 0, (1 - fx) * (1 - fy)), (0, 1, fx * (1 - fy)),
+                           (1, 0, (1 - fx) * fy), (1, 1, fx * fy)):
+            xi, yi = x0 + dx, y0 + dy
+            ok = (xi >= 0) & (xi <= w - 1) & (yi >= 0) & (yi <= h - 1)
+            tap = src[b][:, yi.clamp(0, h - 1).long(), xi.clamp(0, w - 1).long()]
+            out[b] += tap * (wt * ok)
+    return out
+
+
+def test_cost_volume_known_answers():
+    """identity homography => warp == src for every plane; identical
+    views + identity => variance == 0 exactly; gwc with identical views => mean(ref^2)."""
+    g = torch.Generator().manual_seed(0)
+    B, V, C, h, w, D = 2, 3, 16, 40, 56, 8
+    ref = torch.randn(B, 1, C, h, w, generator=g)
+    feats = ref.expand(-1, V, -1, -1, -1).contiguous().to(DEV)
+    eye = torch.eye(3, 4).reshape(1, 1, 3, 4).expand(B, V - 1, -1, -1).contiguous().to(DEV)
+    dv = (400 + 50 * torch.rand(B, D, h, w, generator=g)).to(DEV)
+    wv = ops.homo_warp(feats[:, 1], eye[:, 0], dv)
+    assert torch.equal(wv, feats[:, 1].unsqueeze(2).expand(-1, -1, D, -1, -1))
+    var = ops.warp_cost(feats, eye, dv, 1, ops.NHWC)
+    assert var.abs().max().item() < 2e-6          # Q/V - (S/V)^2 cancels to rounding
+    gwc = ops.warp_cost(feats, eye, dv, 4, ops.NCHW)
+    expect = (feats[:, 0] ** 2).reshape(B, 4, 4, h, w).mean(2).unsqueeze(2).expand(-1, -1, D, -1, -1)
+    assert (gwc - expect).abs().max().item() < 1e-5
+    # projection that puts every sample behind the camera: only the reference contributes
+    behind = eye.clone()
+    behind[:, :, 2, 2] = -1.0
+    var_b = ops.warp_cost(feats, behind, dv, 1, ops.NCHW)
+    r = feats[:, 0].unsqueeze(2)
+    assert torch.allclose(var_b, (r * r / V - (r / V) ** 2).expand(-1, -1, D, -1, -1), atol=1e-6)
+
+
+def test_cost_volume_many_views_and_edges():
+    """generic (runtime-V) path, ragged pixel counts, B>1."""
+    g = torch.Generator().manual_seed(2)
+    for V, C, h, w, D in ((2, 8, 9, 13, 3), (6, 8, 17, 31, 5), (8, 16, 16, 24, 4)):
+        B = 2
+        feats = torch.randn(B, V, C, h, w, generator=g)
+        pm = synth.projection_matrices(V, W=4 * w, H=4 * h, stress=True, behind_view=1)[:, 2]
+        pm = pm.unsqueeze(0).expand(B, -1, -1, -1).contiguous()
+        dv = 430.0 + 20 * torch.arange(D).float().reshape(1, D, 1, 1) + torch.rand(B, D, h, w, generator=g)
+        want = O.variance_cost_volume(feats, pm, dv)
+        got = ops.warp_cost(feats.to(DEV), pm.to(DEV), dv.to(DEV), 1, ops.NHWC).cpu()
+        err = stats(f"var V={V}", got, want)
+        assert err.max() < 1e-4
+
+
+# ----------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("cin", [8, 32])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("tf32", 3e-3)])
+def test_costreg_vs_reference_golden(golden, cin, precision, tol):
+    from casmvsnet_pl_b200 import ABN
+    from casmvsnet_pl_b200.models.mvsnet import CostRegNet
+    g = golden(f"costreg_c{cin}")
+    net = CostRegNet(cin, ABN).eval()
+    net.load_state_dict({k[3:]: v for k, v in g.items() if k.startswith("sd.")})
+    net = net.to(DEV)
+    net.precision = precision
+    y = net(g["x"].to(DEV)).cpu()
+    assert y.shape == g["logits"].shape
+    err = stats(f"costreg c{cin} {precision}", y, g["logits"])
+    # fp32: only accumulation-order differences over K=27*Cin terms (<= 2e-5 of max);
+    # tf32: operands rounded to 10-bit mantissa, 11 layers deep (<= 3e-3 of max)
+    assert err.max() / g["logits"].abs().max() < tol
+
+
+@pytest.mark.parametrize("kind,stride,cin,cout,dims", [
+    ("conv", 1, 8, 8, (4, 6, 10)), ("conv", 1, 16, 16, (3, 5, 7)), ("conv", 1, 64, 64, (2, 4, 5)),
+    ("conv", 1, 8, 1, (4, 6, 9)), ("conv", 2, 8, 16, (8, 8, 16)), ("conv", 2, 32, 64, (4, 6, 6)),
+    ("convT", 2, 64, 32, (1, 3, 5)), ("convT", 2, 16, 8, (4, 5, 6))])
+def test_conv3d_layer_vs_torch_cpu(kind, stride, cin, cout, dims):
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    B = 2
+    x = torch.randn(B, cin, *dims, generator=g)
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    if kind == "conv":
+        wt = torch.randn(cout, cin, 3, 3, 3, generator=g) * 0.1
+        y = F.conv3d(x, wt, None, stride, 1)
+        k = ops.CONV
+    else:
+        wt = torch.randn(cin, cout, 3, 3, 3, generator=g) * 0.1
+        y = F.conv_transpose3d(x, wt, None, stride=2, padding=1, output_padding=1)
+        k = ops.CONV_TRANSPOSE
+    skip = torch.randn_like(y)
+    want = F.leaky_relu(y * scale.reshape(1, -1, 1, 1, 1) + shift.reshape(1, -1, 1, 1, 1), 0.01) + skip
+    wp = ops.pack_conv3d_weight(wt.to(DEV), k)
+    got = ops.conv3d(x.to(DEV), wp, cin, cout, scale.to(DEV), shift.to(DEV), 0.01, skip.to(DEV),
+                     k, stride, ops.FP32).cpu()
+    assert got.shape == want.shape
+    err = stats(f"{kind} s{stride} {cin}->{cout}", got, want)
+    assert err.max() < 2e-5 * max(1.0, want.abs().max().item())
+
+
+# ----------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("D", [8, 32, 48, 64])
+def test_regress_vs_reference_golden(golden, D):
+    g = golden(f"regress_d{D}")
+    depth, conf, index, prob = ops.regress(g["logits"].to(DEV), g["depth_values"].to(DEV),
+                                           want_index=True, want_prob=True)
+    e_d = stats(f"depth D={D}", depth.cpu(), g["depth"])
+    e_c = stats(f"conf  D={D}", conf.cpu(), g["confidence"])
+    e_p = stats(f"prob  D={D}", prob.cpu(), g["prob"])
+    assert (e_d / g["depth"].abs()).max() < 1e-6       # depth <= 1e-6 rel
+    assert e_c.max() < 1e-6 and e_p.max() < 1e-6
+    # index: p differs by exp() ulps, so only pixels whose Σp·d sits within 1e-4 of an
+    # integer may legitimately flip; everything else must be exact
+    frac = (g["prob"] * torch.arange(D).float().reshape(1, D, 1, 1)).sum(1)
+    safe = (frac - frac.round()).abs() > 1e-4
+    assert torch.equal(index.cpu()[safe], g["index"][safe])
+
+
+@pytest.mark.parametrize("D", [8, 32, 48, 64])
+def test_regress_bit_exact_given_identical_prob(golden, D):
+    """north_star: pixel-index regression bit-exact.  Fed the reference's own p, the
+    kernel's cascade-16 summation reproduces torch-CPU bit for bit."""
+    g = golden(f"regress_d{D}")
+    depth, conf, index, _ = ops.regress(g["prob"].to(DEV), g["depth_values"].to(DEV),
+                                        input_is_prob=True, want_index=True)
+    assert torch.equal(index.cpu(), g["index"])
+    assert torch.equal(depth.cpu(), g["depth"])
+    assert torch.equal(conf.cpu(), g["confidence"])
+
+
+def test_depth_regression_api_vector_depths(golden):
+    from casmvsnet_pl_b200.models.modules import depth_regression
+    g = golden("regress_d32")
+    steps = torch.arange(32).float()
+    got = depth_regression(g["prob"].to(DEV), steps.to(DEV)).cpu()
+    want = O.regress_depth(g["logits"], steps)[0]
+    assert torch.equal(got, (g["prob"] * steps.reshape(1, -1, 1, 1)).sum(1))
+    assert torch.allclose(got, want, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------- K4
+def test_hypotheses_bit_exact(golden):
+    from casmvsnet_pl_b200.models.modules import get_depth_values
+    g = golden("hypotheses")
+    cur = g["cur"].to(DEV)
+    assert torch.equal(get_depth_values(cur, 8, 2.65).cpu(), g["hyp_float"])
+    assert torch.equal(get_depth_values(cur, 32, g["interval_tensor"].to(DEV)).cpu(), g["hyp_tensor"])
+    up = ops.depth_hypotheses(g["low"].to(DEV), 32, 2.65 * 2, upsample=True).cpu()
+    err = stats("upsample+ladder", up, g["hyp_up"])
+    assert (err / g["hyp_up"].abs()).max() < 1e-6     # bilinear blend may differ in the last ulp
+    uni = ops.uniform_hypotheses(425.0, 2.65 * 4, 48, 2, 4, 6, DEV).cpu()
+    assert torch.equal(uni, O.initial_hypotheses(425.0, 2.65 * 4, 48, 2, 4, 6).contiguous())
+    uni_t = ops.uniform_hypotheses(torch.tensor([[425.0], [430.0]]), torch.tensor([[10.6], [10.0]]),
+                                   48, 2, 4, 6, DEV).cpu()
+    assert torch.equal(uni_t, O.initial_hypotheses(torch.tensor([[425.0], [430.0]]),
+                                                   torch.tensor([[10.6], [10.0]]), 48, 2, 4, 6).contiguous())
+
+
+def test_layout_helpers_roundtrip():
+    x = torch.randn(3, 16, 7, 11, device=DEV)
+    y = torch.empty(3, 7, 11, 16, device=DEV)
+    lib = _lib.load()
+    s = ops._stream()
+    _lib.check(lib.casmvs_nchw_to_nhwc(ops._ptr(x), ops._ptr(y), 3, 16, 77, s))
+    assert torch.equal(y, x.permute(0, 2, 3, 1))
+    z = torch.empty_like(x)
+    _lib.check(lib.casmvs_nhwc_to_nchw(ops._ptr(y), ops._ptr(z), 3, 16, 77, s))
+    assert torch.equal(z, x)
