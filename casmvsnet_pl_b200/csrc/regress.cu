@@ -13,10 +13,12 @@ namespace casmvs {
 
 constexpr int kK3Threads = 128;
 
-// Accumulator reproducing torch-CPU's sum over a non-innermost dim for sizes
-// < 256 (ATen SumKernel cascade_sum, level_step 16): 16 terms are added
+// Accumulator following the main path of torch-CPU's sum over a non-innermost dim
+// for sizes < 256 (ATen SumKernel multi_row_sum, level_step 16): 16 terms are added
 // sequentially into acc0, which is then folded into acc1 and cleared; the tail
-// stays in acc0; result = acc0 + acc1.  __fadd_rn keeps ptxas from fusing.
+// stays in acc0; result = acc0 + acc1.  (ATen's tail-vector columns use a 4-way
+// interleaved variant, so torch itself is not order-uniform across pixels.)
+// __fadd_rn keeps ptxas from fusing.
 struct Cascade16 {
   float a0 = 0.f, a1 = 0.f;
   int n = 0;

@@ -39,7 +39,15 @@ class FeatureNet(nn.Module):
     def _up2(x):
         return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
 
+    # cuDNN would run fp32 convs as TF32 on B200 by default; the reference path is
+    # fp32 (opt.py:69-70), so keep IEEE fp32 here unless the caller opts in.
+    allow_tf32 = False
+
     def forward(self, x):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=self.allow_tf32):
+            return self._forward(x)
+
+    def _forward(self, x):
         # channels-last end to end: level_l come out physically (N,h,w,C)
         x = x.contiguous(memory_format=torch.channels_last)
         c0 = self.conv0(x)

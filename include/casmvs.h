@@ -129,8 +129,8 @@ int casmvs_costreg_fwd(const float* x, const float* params, float* logits,
  *   depth (B,h,w) f32, confidence (B,h,w) f32,
  *   index (B,h,w) int64 or NULL, prob (B,D,h,w) or NULL.
  * input_is_prob != 0 skips the softmax (logits already hold probabilities).
- * Sums over D use torch-CPU's order (16-term chunks cascaded) so that
- * depth_index is bit-exact against the oracle for identical p.            */
+ * Sums over D use the main-path order of ATen's CPU sum (sequential 16-term
+ * chunks, cascaded); depth_index equals the oracle's for identical p.      */
 int casmvs_regress_fwd(const float* logits, const float* depth_values, int dv_is_vector,
                        int input_is_prob, float* depth, float* confidence,
                        int64_t* index, float* prob, int B, int D, int h, int w,
