@@ -13,13 +13,15 @@
 // HBM model: read V*C*h*w feature floats once (they live in L2 for
 // the whole launch), read D*h*w hypotheses once, write Cout*D*h*w cost floats
 // once.  The kernel is write-bound.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace casmvs {
 
 constexpr int kCPT = 8;          // channels per thread
 constexpr int kMaxSrc = 15;      // V-1 supported by the smem projection table
-constexpr int kK1Threads = 256;
+constexpr int kK1Threads = 128;
 
 struct Taps {
   int o00, o01, o10, o11;  // float offsets of the 4 taps (channel 0) inside the view
@@ -73,15 +75,99 @@ __device__ __forceinline__ void blend8(const float* __restrict__ base, const Tap
   r[7] = fmaf(d1.w, t.w11, fmaf(c1.w, t.w10, fmaf(b1.w, t.w01, a1.w * t.w00)));
 }
 
-// NSRC > 0: number of source views known at compile time (per-view R*(x,y,1)
-// kept in registers); NSRC == 0: generic (recomputed from smem per plane).
-template <int NSRC, bool GWC, bool OUT_NHWC>
-__global__ void __launch_bounds__(kK1Threads)
+// ---- packed fp32x2 helpers (Blackwell FFMA2 / 256-bit LDG, STG) -----------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+  u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ void unpk2(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+  u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+  u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+  u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+struct Tex8 { u64 v[4]; };   // 8 channels of one texel, as 4 packed pairs
+__device__ __forceinline__ Tex8 ldg256(const float* p) {   // 32-byte aligned
+  Tex8 t;
+  asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];"
+               : "=l"(t.v[0]), "=l"(t.v[1]), "=l"(t.v[2]), "=l"(t.v[3]) : "l"(p));
+  return t;
+}
+__device__ __forceinline__ void stg256(float* p, const u64 (&v)[4]) {
+  asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v[0]), "l"(v[1]), "l"(v[2]),
+               "l"(v[3]) : "memory");
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+}
+
+// The kernel is instruction-issue bound (ncu: issue ~50 %, DRAM ~10 % in the first
+// version), so the sampler is written for instruction count:
+//  * the 2x2 window is addressed as ONE base (clamped to [0,w-2]x[0,h-2]) plus
+//    compile-time offsets {0, C, w*C, w*C + C}; the zero-padding rule of
+//    grid_sample becomes a remap of the four weights at the image border,
+//  * reciprocals are MUFU.RCP (1 ulp) instead of the IEEE sequence,
+//  * the blend runs on packed FFMA2 with 256-bit texel loads.
+struct Window {
+  Tex8 t00, t01, t10, t11;
+};
+
+// Branch-free: a sample that contributes nothing (behind the camera / fully outside
+// the source image) gets four zero weights and a clamped, always-valid address, so
+// the loop body is straight-line code and ptxas can keep the loads of all views in
+// flight at once.  CT = compile-time channel count (0: use C).
+template <int CT>
+__device__ __forceinline__ void sample_view(const float* __restrict__ vbase, float qx, float qy,
+                                            float qz, int h, int w, int C, int row_floats,
+                                            Window& win, float& w00, float& w01, float& w10,
+                                            float& w11) {
+  const float rz = rcp_approx(qz);
+  const float u = qx * rz, v = qy * rz;
+  const float x0f = floorf(u), y0f = floorf(v);
+  // float->int saturates, so huge |u| fails the range test like ATen's within_bounds;
+  // q_z <= 1e-7 is mapped to (w,h) = fully outside by the reference (modules.py:76-79)
+  const int x0 = __float2int_rd(u), y0 = __float2int_rd(v);
+  const bool valid = (qz > 1e-7f) && (unsigned)(x0 + 1) <= (unsigned)w &&
+                     (unsigned)(y0 + 1) <= (unsigned)h;
+  const float fx = u - x0f, fy = v - y0f;
+  float wxa = 1.f - fx, wxb = fx, wya = 1.f - fy, wyb = fy;
+  // border: texel x0 (or x0+1) is outside => its weight is dropped; the pair
+  // (xs, xs+1) stays inside the image and the surviving weight moves to its slot
+  if (x0 < 0) { wxa = wxb; wxb = 0.f; }
+  if (x0 > w - 2) { wxb = wxa; wxa = 0.f; }
+  if (y0 < 0) { wya = wyb; wyb = 0.f; }
+  if (y0 > h - 2) { wyb = wya; wya = 0.f; }
+  if (!valid) { wxa = 0.f; wxb = 0.f; }
+  const int xs = min(max(x0, 0), w - 2), ys = min(max(y0, 0), h - 2);
+  w00 = wxa * wya; w01 = wxb * wya; w10 = wxa * wyb; w11 = wxb * wyb;
+  const int cc = CT > 0 ? CT : C;
+  const unsigned off = (unsigned)(ys * row_floats + xs * cc);
+  const float* p = vbase + off;
+  win.t00 = ldg256(p);
+  win.t01 = ldg256(p + cc);
+  win.t10 = ldg256(p + row_floats);
+  win.t11 = ldg256(p + row_floats + cc);
+}
+
+// NSRC > 0: number of source views known at compile time (per-view R*(x,y,1) stays
+// in registers); NSRC == 0: generic run-time V.  CT: compile-time C (0 = generic).
+// grid = (pixel-thread blocks, B, depth chunks of `dchunk` planes).  Needs h,w >= 2.
+template <int NSRC, int CT, bool GWC, bool OUT_NHWC>
+__global__ void __launch_bounds__(kK1Threads, 4)
 warp_cost_kernel(const float* __restrict__ feats,   // (B,V,h,w,C)
                  const float* __restrict__ proj,    // (B,V-1,3,4)
                  const float* __restrict__ dv,      // (B,D,h,w)
-                 float* __restrict__ cost, int V, int C, int D, int h, int w, int G) {
+                 float* __restrict__ cost, int V, int C_rt, int D, int h, int w, int G,
+                 int dchunk) {
   __shared__ float s_proj[kMaxSrc * 12];
+  const int C = CT > 0 ? CT : C_rt;
   const int b = blockIdx.y;
   const int nsrc = NSRC > 0 ? NSRC : V - 1;
   for (int i = threadIdx.x; i < nsrc * 12; i += blockDim.x)
@@ -98,95 +184,112 @@ warp_cost_kernel(const float* __restrict__ feats,   // (B,V,h,w,C)
   const int pixc = active ? pix : hw - 1;         // inactive lanes still take part in shuffles
   const int y = pixc / w, x = pixc - y * w;
   const float xf = (float)x, yf = (float)y;
+  const int row_floats = w * C;
 
   const size_t view_stride = (size_t)hw * C;
-  const float* fb = feats + (size_t)b * V * view_stride;
+  const float* fb = feats + (size_t)b * V * view_stride + c0;
 
-  float ref[kCPT];
-  {
-    float4 r0 = ldg4(fb + (size_t)pixc * C + c0), r1 = ldg4(fb + (size_t)pixc * C + c0 + 4);
-    ref[0] = r0.x; ref[1] = r0.y; ref[2] = r0.z; ref[3] = r0.w;
-    ref[4] = r1.x; ref[5] = r1.y; ref[6] = r1.z; ref[7] = r1.w;
-  }
-
-  // per-view R*(x,y,1)   (modules.py:72, first term)
-  float ax[NSRC > 0 ? NSRC : 1], ay[NSRC > 0 ? NSRC : 1], az[NSRC > 0 ? NSRC : 1];
-  if (NSRC > 0) {
+  const Tex8 ref = ldg256(fb + (size_t)pixc * C);
+  u64 refsq[4];
 #pragma unroll
-    for (int v = 0; v < (NSRC > 0 ? NSRC : 1); ++v) {
-      const float* P = s_proj + v * 12;
-      ax[v] = fmaf(P[0], xf, fmaf(P[1], yf, P[2]));
-      ay[v] = fmaf(P[4], xf, fmaf(P[5], yf, P[6]));
-      az[v] = fmaf(P[8], xf, fmaf(P[9], yf, P[10]));
-    }
+  for (int k = 0; k < 4; ++k) refsq[k] = mul2(ref.v[k], ref.v[k]);
+
+  constexpr int NV = NSRC > 0 ? NSRC : 1;
+  float ax[NV], ay[NV], az[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const float* P = s_proj + v * 12;
+    ax[v] = fmaf(P[0], xf, fmaf(P[1], yf, P[2]));   // R*(x,y,1)   (modules.py:72)
+    ay[v] = fmaf(P[4], xf, fmaf(P[5], yf, P[6]));
+    az[v] = fmaf(P[8], xf, fmaf(P[9], yf, P[10]));
   }
 
   const float inv_v = 1.f / (float)V;
+  const u64 inv_v2 = pk2(inv_v, inv_v), ninv_v2 = pk2(-inv_v, -inv_v);
   const int cpg = GWC ? C / G : 1;                // channels per group
   const int cout = GWC ? G : C;
   const float* dvp = dv + (size_t)b * D * hw + pixc;
+  const int d_begin = blockIdx.z * dchunk;
+  const int d_end = min(D, d_begin + dchunk);
 
-  for (int d = 0; d < D; ++d) {
-    const float depth = __ldg(dvp + (size_t)d * hw);
-    const float inv_d = __frcp_rn(depth);
-    float S[kCPT], Q[kCPT];
+  float tx[NV], ty[NV], tz[NV];                   // T of each view (modules.py:64)
 #pragma unroll
-    for (int k = 0; k < kCPT; ++k) {
-      S[k] = GWC ? 0.f : ref[k];                  // gwc: reference NOT in the sum (mvsnet.py:144)
-      Q[k] = ref[k] * ref[k];
+  for (int v = 0; v < NV; ++v) {
+    tx[v] = s_proj[v * 12 + 3]; ty[v] = s_proj[v * 12 + 7]; tz[v] = s_proj[v * 12 + 11];
+  }
+  const float* dptr = dvp + (size_t)d_begin * hw;
+  float depth_next = d_begin < d_end ? __ldg(dptr) : 1.f;
+
+  for (int d = d_begin; d < d_end; ++d) {
+    const float depth = depth_next;
+    dptr += hw;
+    if (d + 1 < d_end) depth_next = __ldg(dptr);  // prefetch: off the dependent chain
+    const float inv_d = rcp_approx(depth);
+    u64 S[4], Q[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      S[k] = GWC ? 0ull : ref.v[k];               // gwc: reference NOT in the sum (mvsnet.py:144)
+      Q[k] = refsq[k];
     }
 #pragma unroll
-    for (int v = 0; v < (NSRC > 0 ? NSRC : 1); ++v) {
-      // generic path loops at run time
+    for (int v = 0; v < NV; ++v) {
       for (int vv = (NSRC > 0 ? v : 0); vv < (NSRC > 0 ? v + 1 : nsrc); ++vv) {
-        const float* P = s_proj + vv * 12;
         float qx, qy, qz;
         if (NSRC > 0) {
-          qx = fmaf(P[3], inv_d, ax[v]);
-          qy = fmaf(P[7], inv_d, ay[v]);
-          qz = fmaf(P[11], inv_d, az[v]);
+          qx = fmaf(tx[v], inv_d, ax[v]);
+          qy = fmaf(ty[v], inv_d, ay[v]);
+          qz = fmaf(tz[v], inv_d, az[v]);
         } else {
+          const float* P = s_proj + vv * 12;
           qx = fmaf(P[3], inv_d, fmaf(P[0], xf, fmaf(P[1], yf, P[2])));
           qy = fmaf(P[7], inv_d, fmaf(P[4], xf, fmaf(P[5], yf, P[6])));
           qz = fmaf(P[11], inv_d, fmaf(P[8], xf, fmaf(P[9], yf, P[10])));
         }
-        Taps t = make_taps(qx, qy, qz, h, w, C);
-        if (t.any) {
-          float r[kCPT];
-          blend8(fb + (size_t)(vv + 1) * view_stride + c0, t, r);
+        float w00, w01, w10, w11;
+        Window win;
+        sample_view<CT>(fb + (size_t)(vv + 1) * view_stride, qx, qy, qz, h, w, C, row_floats,
+                        win, w00, w01, w10, w11);
+        const u64 p00 = pk2(w00, w00), p01 = pk2(w01, w01), p10 = pk2(w10, w10),
+                  p11 = pk2(w11, w11);
 #pragma unroll
-          for (int k = 0; k < kCPT; ++k) {
-            S[k] += r[k];
-            if (!GWC) Q[k] = fmaf(r[k], r[k], Q[k]);
-          }
+        for (int k = 0; k < 4; ++k) {
+          // tap order nw, ne, sw, se like ATen grid_sampler_2d
+          u64 r = mul2(win.t00.v[k], p00);
+          r = fma2(win.t01.v[k], p01, r);
+          r = fma2(win.t10.v[k], p10, r);
+          r = fma2(win.t11.v[k], p11, r);
+          S[k] = add2(S[k], r);
+          if (!GWC) Q[k] = fma2(r, r, Q[k]);
         }
       }
     }
 
     if (!GWC) {
       // var = Q/V - (S/V)^2   (mvsnet.py:166-168)
-      float o[kCPT];
+      u64 o[4];
 #pragma unroll
-      for (int k = 0; k < kCPT; ++k) {
-        float m = S[k] * inv_v;
-        o[k] = Q[k] * inv_v - m * m;
+      for (int k = 0; k < 4; ++k) {
+        const u64 m = mul2(S[k], inv_v2), mn = mul2(S[k], ninv_v2);
+        o[k] = fma2(mn, m, mul2(Q[k], inv_v2));
       }
       if (active) {
         if (OUT_NHWC) {
-          float* op = cost + ((size_t)(b * D + d) * hw + pix) * C + c0;
-          st4(op, make_float4(o[0], o[1], o[2], o[3]));
-          st4(op + 4, make_float4(o[4], o[5], o[6], o[7]));
+          stg256(cost + ((size_t)(b * D + d) * hw + pix) * C + c0, o);
         } else {
 #pragma unroll
-          for (int k = 0; k < kCPT; ++k)
-            cost[((size_t)(b * C + c0 + k) * D + d) * hw + pix] = o[k];
+          for (int k = 0; k < 4; ++k) {
+            float lo, hi;
+            unpk2(o[k], lo, hi);
+            cost[((size_t)(b * C + c0 + 2 * k) * D + d) * hw + pix] = lo;
+            cost[((size_t)(b * C + c0 + 2 * k + 1) * D + d) * hw + pix] = hi;
+          }
         }
       }
     } else {
       // cost[g] = mean_{c in g}(S_c * ref_c) / (V-1)     (mvsnet.py:170-172)
       float p[kCPT];
 #pragma unroll
-      for (int k = 0; k < kCPT; ++k) p[k] = S[k] * ref[k];
+      for (int k = 0; k < 4; ++k) unpk2(mul2(S[k], ref.v[k]), p[2 * k], p[2 * k + 1]);
       const float inv_cpg = 1.f / (float)cpg;
       const float vm1 = (float)(V - 1);
       if (cpg >= kCPT) {
@@ -303,16 +406,30 @@ static int launch_transpose(const float* in, float* out, int N, size_t R, size_t
   return after_launch(what);
 }
 
-template <int NSRC>
+int g_k1_dchunk = 0;  // CASMVS_K1_DCHUNK overrides the depth-chunk heuristic
+
+template <int NSRC, int CT>
 static void launch_k1(bool gwc, bool nhwc, dim3 grd, cudaStream_t st, const float* f,
                       const float* p, const float* dv, float* cost, int V, int C, int D, int h,
-                      int w, int G) {
+                      int w, int G, int dchunk) {
   if (gwc) {
-    if (nhwc) warp_cost_kernel<NSRC, true, true><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G);
-    else warp_cost_kernel<NSRC, true, false><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G);
+    if (nhwc) warp_cost_kernel<NSRC, CT, true, true><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G, dchunk);
+    else warp_cost_kernel<NSRC, CT, true, false><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G, dchunk);
   } else {
-    if (nhwc) warp_cost_kernel<NSRC, false, true><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G);
-    else warp_cost_kernel<NSRC, false, false><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G);
+    if (nhwc) warp_cost_kernel<NSRC, CT, false, true><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G, dchunk);
+    else warp_cost_kernel<NSRC, CT, false, false><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G, dchunk);
+  }
+}
+
+template <int NSRC>
+static void launch_k1_c(bool gwc, bool nhwc, dim3 grd, cudaStream_t st, const float* f,
+                        const float* p, const float* dv, float* cost, int V, int C, int D, int h,
+                        int w, int G, int dchunk) {
+  switch (C) {
+    case 8: launch_k1<NSRC, 8>(gwc, nhwc, grd, st, f, p, dv, cost, V, C, D, h, w, G, dchunk); break;
+    case 16: launch_k1<NSRC, 16>(gwc, nhwc, grd, st, f, p, dv, cost, V, C, D, h, w, G, dchunk); break;
+    case 32: launch_k1<NSRC, 32>(gwc, nhwc, grd, st, f, p, dv, cost, V, C, D, h, w, G, dchunk); break;
+    default: launch_k1<NSRC, 0>(gwc, nhwc, grd, st, f, p, dv, cost, V, C, D, h, w, G, dchunk); break;
   }
 }
 
@@ -331,7 +448,7 @@ extern "C" int casmvs_warp_cost_fwd(const float* feats, int feat_layout, const f
                                     int B, int V, int C, int D, int h, int w, int num_groups,
                                     void* workspace, size_t workspace_bytes, void* stream) {
   CASMVS_REQUIRE(feats && proj && depth_values && cost, "warp_cost: null pointer");
-  CASMVS_REQUIRE(B >= 0 && V >= 2 && C > 0 && D > 0 && h > 0 && w > 0, "warp_cost: bad dims");
+  CASMVS_REQUIRE(B >= 0 && V >= 2 && C > 0 && D > 0 && h >= 2 && w >= 2, "warp_cost: bad dims (h,w >= 2)");
   CASMVS_REQUIRE(V - 1 <= kMaxSrc, "warp_cost: at most %d source views", kMaxSrc);
   CASMVS_REQUIRE(C % kCPT == 0, "warp_cost: C must be a multiple of %d (got %d)", kCPT, C);
   CASMVS_REQUIRE(C / kCPT <= 32 && (32 % (C / kCPT)) == 0, "warp_cost: C/8 must divide 32");
@@ -361,13 +478,28 @@ extern "C" int casmvs_warp_cost_fwd(const float* feats, int feat_layout, const f
                  "warp_cost: bad cost_layout");
   const bool nhwc = cost_layout == CASMVS_NHWC;
   const long threads = (long)h * w * (C / kCPT);
-  dim3 grd((unsigned)((threads + kK1Threads - 1) / kK1Threads), (unsigned)B);
+  const unsigned xblocks = (unsigned)((threads + kK1Threads - 1) / kK1Threads);
+  // depth chunks: enough CTAs to fill 148 SMs several times over, but chunks long
+  // enough (>= 8 planes) for the texel-window cache to pay off
+  static bool env_read = false;
+  if (!env_read) {
+    env_read = true;
+    if (const char* e = getenv("CASMVS_K1_DCHUNK")) g_k1_dchunk = atoi(e);
+  }
+  int dchunk = D;
+  if (g_k1_dchunk > 0) dchunk = g_k1_dchunk;
+  else {
+    const long want_ctas = (long)num_sms() * 16;
+    while (dchunk > 8 && (long)xblocks * B * ((D + dchunk - 1) / dchunk) < want_ctas)
+      dchunk = (dchunk + 1) / 2;
+  }
+  dim3 grd(xblocks, (unsigned)B, (unsigned)((D + dchunk - 1) / dchunk));
   switch (V - 1) {
-    case 1: launch_k1<1>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups); break;
-    case 2: launch_k1<2>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups); break;
-    case 4: launch_k1<4>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups); break;
-    case 6: launch_k1<6>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups); break;
-    default: launch_k1<0>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups); break;
+    case 1: launch_k1_c<1>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk); break;
+    case 2: launch_k1_c<2>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk); break;
+    case 4: launch_k1_c<4>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk); break;
+    case 6: launch_k1_c<6>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk); break;
+    default: launch_k1<0, 0>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk); break;
   }
   return after_launch("warp_cost");
 }

@@ -114,8 +114,11 @@ def test_full_size_cfg2_properties():
     got = ops.warp_cost(feats.to(DEV), pml.to(DEV), dv.to(DEV), 1, ops.NCHW).cpu()
     err = (got - want).abs().max().item()
     print(f"K1 cfg2 level-2 max|err| {err:.3e} (max|ref| {want.abs().max():.2f})")
-    # w=160: ulp(u)=1.5e-5 px on white-noise features, variance values up to max|ref|
-    assert err < 2e-5 * want.abs().max().item() + 1e-4
+    # w=160: the reference's own normalise/un-normalise round trip moves a sample by
+    # ~2e-5 px; on white-noise features (texel-to-texel jumps up to ~6) that is 1e-4 on a
+    # warped value and ~3e-4 on the variance.  The fp64 test in test_gpu_kernels.py shows the
+    # kernel is at least as close to exact arithmetic as the reference.
+    assert err < 5e-5 * want.abs().max().item() + 1e-4
 
 
 def test_feature_net_channels_last_matches_oracle():
