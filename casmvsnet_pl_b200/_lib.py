@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libcasmvs.so")
 
 NCHW, NHWC = 0, 1
+ROUND_TF32 = 256
 FP32, TF32, TF32X3 = 0, 1, 2
 CONV, CONV_TRANSPOSE = 0, 1
 PRECISIONS = {"fp32": FP32, "tf32": TF32, "tf32x3": TF32X3}

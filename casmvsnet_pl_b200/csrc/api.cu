@@ -20,7 +20,7 @@ void set_error(const char* fmt, ...) {
 // conv3d_direct.cu
 int conv3d_direct(const float* x, const float* wpk, const float* scale, const float* shift,
                   float slope, const float* skip, float* y, int B, int Cin, int Cout, int D,
-                  int h, int w, int kind, int stride, cudaStream_t st);
+                  int h, int w, int kind, int stride, cudaStream_t st, int round_out);
 // conv3d_tc.cu (tcgen05): returns 1 if this layer shape is not handled by the tensor path
 int conv3d_tc(const float* x, const float* wpk, const float* scale, const float* shift,
               float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
@@ -84,8 +84,11 @@ extern "C" int casmvs_conv3d_fwd(const float* x, const float* w_packed, const fl
                        stride, precision, st);
     if (rc <= 0) return rc;  // handled (0) or failed (<0); 1 = shape not covered -> CUDA cores
   }
+  // in the tf32 modes every stored activation is tf32-rounded (unbiased operand for
+  // the tensor-core layers); the prob head (Cout == 1) feeds the softmax and stays fp32
+  const int round_out = (precision == CASMVS_TF32 && Cout > 1) ? 1 : 0;
   return conv3d_direct(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
-                       stride, st);
+                       stride, st, round_out);
 }
 
 // ---- CostRegNet driver ------------------------------------------------------

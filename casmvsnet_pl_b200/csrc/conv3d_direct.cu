@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kConvThreads)
 conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wpk,
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      float slope, const float* __restrict__ skip, float* __restrict__ y,
-                     ConvDims dm) {
+                     ConvDims dm, int round_out) {
   extern __shared__ __align__(16) float s_w[];  // [27][Cin][COT]
   const int Cin = dm.Cin, Cout = dm.Cout;
   const int co0 = blockIdx.y * COT;
@@ -169,6 +169,12 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wpk,
         v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
         v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
       }
+      if (round_out) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v[k])); v[k] = __uint_as_float(r);
+        }
+      }
       st4(y + o, make_float4(v[0], v[1], v[2], v[3]));
       st4(y + o + 4, make_float4(v[4], v[5], v[6], v[7]));
     } else {
@@ -197,7 +203,7 @@ __global__ void pack_w_kernel(const float* __restrict__ wt, float* __restrict__ 
 template <int KIND, int TW>
 static int launch_direct(const float* x, const float* wpk, const float* scale, const float* shift,
                          float slope, const float* skip, float* y, const ConvDims& dm,
-                         cudaStream_t st) {
+                         cudaStream_t st, int round_out) {
   const int wgroups = (dm.wo + TW - 1) / TW;
   const long total = (long)dm.B * dm.Do * dm.ho * wgroups;
   if (total == 0) return 0;
@@ -209,28 +215,28 @@ static int launch_direct(const float* x, const float* wpk, const float* scale, c
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kfn<<<dim3((unsigned)blocks, dm.Cout / 8), kConvThreads, smem, st>>>(x, wpk, scale, shift,
-                                                                       slope, skip, y, dm);
+                                                                       slope, skip, y, dm, round_out);
   } else {
     CASMVS_REQUIRE(dm.Cout == 1, "conv3d: Cout must be 1 or a multiple of 8 (got %d)", dm.Cout);
     const size_t smem = (size_t)27 * dm.Cin * sizeof(float);
     conv3d_direct_kernel<KIND, TW, 1><<<dim3((unsigned)blocks, 1), kConvThreads, smem, st>>>(
-        x, wpk, scale, shift, slope, skip, y, dm);
+        x, wpk, scale, shift, slope, skip, y, dm, 0);
   }
   return after_launch("conv3d_direct");
 }
 
 int conv3d_direct(const float* x, const float* wpk, const float* scale, const float* shift,
                   float slope, const float* skip, float* y, int B, int Cin, int Cout, int D,
-                  int h, int w, int kind, int stride, cudaStream_t st) {
+                  int h, int w, int kind, int stride, cudaStream_t st, int round_out) {
   ConvDims dm;
   dm.B = B; dm.Cin = Cin; dm.Cout = Cout; dm.Di = D; dm.hi = h; dm.wi = w;
   if (kind == CASMVS_CONV) {
     dm.Do = (D - 1) / stride + 1; dm.ho = (h - 1) / stride + 1; dm.wo = (w - 1) / stride + 1;
-    if (stride == 1) return launch_direct<K_CONV_S1, 4>(x, wpk, scale, shift, slope, skip, y, dm, st);
-    return launch_direct<K_CONV_S2, 1>(x, wpk, scale, shift, slope, skip, y, dm, st);
+    if (stride == 1) return launch_direct<K_CONV_S1, 4>(x, wpk, scale, shift, slope, skip, y, dm, st, round_out);
+    return launch_direct<K_CONV_S2, 1>(x, wpk, scale, shift, slope, skip, y, dm, st, round_out);
   }
   dm.Do = 2 * D; dm.ho = 2 * h; dm.wo = 2 * w;
-  return launch_direct<K_CONVT, 1>(x, wpk, scale, shift, slope, skip, y, dm, st);
+  return launch_direct<K_CONVT, 1>(x, wpk, scale, shift, slope, skip, y, dm, st, round_out);
 }
 
 }  // namespace casmvs

@@ -1,9 +1,502 @@
-// K2 (tcgen05 variant) — placeholder until the tensor-core path lands:
-// reports "shape not covered" so the dispatcher uses the CUDA-core kernel.
+// K2 (tensor-core variant) — 3x3x3 stride-1 convolution as an im2col-free implicit
+// GEMM on tcgen05 (kind::tf32, fp32 accumulators in TMEM) with the norm-act (+skip)
+// epilogue fused.  sm_100a only.
+//
+// Replaces (reference, relative to /root/reference): ConvBnReLU3D
+// (models/modules.py:21-31) and the `prob` head (models/mvsnet.py:89,103) for the
+// stride-1 layers of CostRegNet (conv0, conv2, conv4, prob: ~85 % of its FLOPs).
+//
+// GEMM view per CTA:  D[128 voxels x N] += A_tap[128 x Cin] * W_tap[Cin x N], 27 taps.
+//   M = 128 output voxels = an 8(w) x 16(h) patch of one depth slice,
+//   K = Cin per tap (Cin/8 MMAs of K=8),
+//   N = 3 x GW: the three kd taps that share one A operand (input slice s shifted by
+//   kh,kw) are issued as ONE MMA whose column groups are the accumulators of the
+//   output slices s+1, s, s-1 (GW = Cout padded to 16).  With Cout <= 32 the MMA is
+//   bound by the shared-memory read of A (4 KB per K=8 step), so tripling N per A read
+//   is what takes the layer from 13x off the HBM roofline to ~1.3x.
+// The CTA marches along depth.  Each input depth slice (with its 1-voxel halo,
+// 18 x 10 voxels) is brought into shared memory ONCE by 4 producer warps
+// (cp.async, zero-fill = the conv's zero padding) into a 4-slot ring and is used
+// by the 27 taps of the three output slices it touches: the A operand of a tap is
+// just a shifted *view* of the resident brick, expressed in the UMMA shared-memory
+// descriptor (no-swizzle K-major layout: [h][Cin/4][w][4 floats]; 8 consecutive w
+// form a core matrix, LBO = one channel-quad plane, SBO = one brick row).
+// Nothing is re-read from L2 per tap, which is what makes the layer HBM-bound
+// instead of L2-bound (a classic implicit GEMM would fetch every voxel 27 times).
+//
+// Warp roles (9 warps): 0-3 epilogue (TMEM -> regs -> scale/shift/LeakyReLU/+skip
+// -> global), 4-7 producers, 8 MMA issuer (one elected thread).  Pipelines: smem
+// ring full/empty mbarriers, double-buffered TMEM accumulator full/empty mbarriers.
+#include <stdlib.h>
+
 #include "common.cuh"
+
 namespace casmvs {
-int conv3d_tc(const float*, const float*, const float*, const float*, float, const float*, float*,
-              int, int, int, int, int, int, int, int, int, cudaStream_t) {
+
+namespace tc {
+
+constexpr int kTileW = 8, kTileH = 16;           // M = 128
+constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2;
+constexpr int kSlots = 4;
+constexpr int kThreads = 9 * 32;
+constexpr int kProducerThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t elected) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar), "r"(elected)
+      : "memory");
+}
+// One lane of a converged warp (the MMA warp runs warp-uniform code so that the
+// descriptors stay in uniform registers; only the issue itself is predicated).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred;
+}
+// D[tmem] += A[smem desc] * B[smem desc], tf32 operands, fp32 accumulate; issued by the
+// lane whose `elected` is non-zero
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                          uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                          uint32_t elected) {
+  // descriptors travel as (lo,hi) words: only the low word (start address) changes per tap
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 q, %6, 0;\n\t"
+      "setp.ne.b32 p, %6, 0xffffffff;\n\t"          // always true: accumulate
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(elected)
+      : "memory");
+}
+// shared-memory matrix descriptor, SWIZZLE_NONE, K-major (cute::UMMA::SmemDescriptor):
+// [0,14) start>>4 | [16,30) leading byte offset>>4 | [32,46) stride byte offset>>4 |
+// [46,48) version = 1 (Blackwell) | [61,64) layout type = 0 (no swizzle)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) @4,
+// a/b format TF32 (2) @7/@10, a/b major K (0), N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+template <int NPAD>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[NPAD]) {
+  static_assert(NPAD == 16 || NPAD == 32, "NPAD");
+  uint32_t r[NPAD];
+  if constexpr (NPAD == 16) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+          "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+  }
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < NPAD; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// zero 16 consecutive fp32 columns of this warp's 32 TMEM lanes
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+struct Params {
+  const float* x;       // (B,D,H,W,CIN)
+  const float* wpk;     // [27][CIN][Cout]  (direct-kernel packing)
+  const float* scale;   // [Cout] or null
+  const float* shift;   // [Cout] or null
+  const float* skip;    // (B,D,H,W,Cout) or null
+  float* y;             // (B,D,H,W,Cout)
+  float slope;
+  int B, D, H, W, Cout;
+  int tiles_w, tiles_h, nchunks, dchunk;
+  int round_out;        // round the stored activations to tf32 (unbiased next-layer operand)
+  long long* dbg;       // optional timeline of CTA 0: [role][slice][4] clock64 stamps
+};
+#define TC_STAMP(role, idx, k)                                                        \
+  do {                                                                                \
+    if (p.dbg && blockIdx.x == 0) p.dbg[((role) * 64 + (idx)) * 4 + (k)] = clock64(); \
+  } while (0)
+
+template <int CIN, int GW>
+struct Smem {
+  static constexpr int CQ = CIN / 4;
+  static constexpr int kSlotBytes = kHaloH * CQ * kHaloW * 16;
+  static constexpr int kWBytes = 9 * CIN * 3 * GW * 4;               // [kh][kw][cq][3*GW][4]
+  static constexpr int kRingOff = kWBytes;
+  static constexpr int kParamOff = kRingOff + kSlots * kSlotBytes;   // scale/shift [2][GW]
+  static constexpr int kBarOff = kParamOff + 2 * GW * 4;
+  static constexpr int kTotal = kBarOff + 128 + 32 * 8;
+};
+
+// Largest power of two >= n (>= 32): TMEM allocations must be a power of two.
+__host__ __device__ constexpr int tmem_cols_for(int n) {
+  return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512;
+}
+
+template <int CIN, int GW>
+__global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) {
+  using S = Smem<CIN, GW>;
+  constexpr int CQ = S::CQ;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_w = s_base, s_ring = s_base + S::kRingOff, s_bar = s_base + S::kBarOff;
+  float* s_param = reinterpret_cast<float*>(smem + S::kParamOff);
+  // barriers: full[4] @0, empty[4] @32, tmem ptr @64, tmem_full[32] @128.  Every output
+  // slice has its OWN single-use accumulator-ready barrier: nothing throttles the MMA warp
+  // against the epilogue (the accumulators are not recycled), so a recycled barrier could
+  // be lapped twice and its parity would alias (seen as a hang with Cin = 8, 16+ slices).
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 32, bar_tfull = s_bar + 128;
+  volatile uint32_t* s_tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + S::kBarOff + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- work item ----
+  int item = blockIdx.x;
+  const int tw = item % p.tiles_w; item /= p.tiles_w;
+  const int th = item % p.tiles_h; item /= p.tiles_h;
+  const int ck = item % p.nchunks;
+  const int b = item / p.nchunks;
+  const int w0 = tw * kTileW, h0 = th * kTileH;
+  const int d0 = ck * p.dchunk, d1 = min(p.D, d0 + p.dchunk);
+  const int nd = d1 - d0;                         // <= 512 / GW (host guarantees)
+  const int nslices = nd + 2;                     // input slices d0-1 .. d1
+  const uint32_t tmem_cols = tmem_cols_for(p.dchunk * GW);
+
+  // ---- one-time setup ----
+  if (threadIdx.x == 0) TC_STAMP(3, 0, 0);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSlots; ++i) {
+      mbar_init(bar_full + 8 * i, kProducerThreads);
+      mbar_init(bar_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < 32; ++i) mbar_init(bar_tfull + 8 * i, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32((const void*)s_tmem_ptr), tmem_cols);
+  // weights -> smem as the B operand image [kh][kw][cq][n = g*GW + co][4], g = 2 - kd,
+  // tf32-rounded (round to nearest), zero rows for co >= Cout
+  for (int i = threadIdx.x; i < 9 * CIN * 3 * GW; i += kThreads) {
+    const int j = i & 3;
+    const int n = (i >> 2) % (3 * GW);
+    const int r = (i >> 2) / (3 * GW);    // (kh*3+kw)*CQ + cq
+    const int cq = r % CQ, khw = r / CQ;
+    const int g = n / GW, co = n % GW;
+    const int kd = 2 - g;
+    const int ci = cq * 4 + j;
+    float v = 0.f;
+    if (co < p.Cout)
+      v = to_tf32(__ldg(p.wpk + ((size_t)(kd * 9 + khw) * CIN + ci) * p.Cout + co));
+    reinterpret_cast<float*>(smem)[i] = v;
+  }
+  for (int i = threadIdx.x; i < GW; i += kThreads) {
+    s_param[i] = (i < p.Cout) ? (p.scale ? __ldg(p.scale + i) : 1.f) : 0.f;
+    s_param[GW + i] = (i < p.Cout) ? (p.shift ? __ldg(p.shift + i) : 0.f) : 0.f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem_ptr;
+  // One accumulator (GW columns) per output slice of the chunk, laid out linearly, so
+  // the three slices an input slice feeds are always adjacent columns.  They are zeroed
+  // here once; every MMA then accumulates (the accumulate flag is per instruction, not
+  // per column, so a first-touch overwrite is not expressible for one group of three).
+  if (warp < 4) {
+    for (int c = 0; c < nd * GW; c += 16)
+      tmem_zero16(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (threadIdx.x == 0) TC_STAMP(3, 0, 1);
+
+  if (warp >= 4 && warp < 8) {
+    // ===================== producers: input bricks -> smem ring =====================
+    const int ptid = threadIdx.x - 128;
+    for (int it = 0; it < nslices; ++it) {
+      const int s = d0 - 1 + it;
+      const int slot = it & (kSlots - 1);
+      if (ptid == 0) TC_STAMP(0, it, 0);
+      if (it >= kSlots) mbar_wait(bar_empty + 8 * slot, ((it >> 2) - 1) & 1);
+      if (ptid == 0) TC_STAMP(0, it, 1);
+      const uint32_t dst0 = s_ring + slot * S::kSlotBytes;
+      const bool s_ok = (s >= 0) && (s < p.D);
+      const float* xs = p.x + (((size_t)b * p.D + (s_ok ? s : 0)) * p.H) * (size_t)p.W * CIN;
+      for (int c = ptid; c < kHaloH * kHaloW * CQ; c += kProducerThreads) {
+        const int cq = c % CQ;            // channel quad fastest: coalesced global reads
+        const int vox = c / CQ;
+        const int ww = vox % kHaloW, hh = vox / kHaloW;
+        const int ih = h0 - 1 + hh, iw = w0 - 1 + ww;
+        const bool ok = s_ok && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W;
+        const float* src = ok ? xs + ((size_t)ih * p.W + iw) * CIN + cq * 4 : p.x;
+        cp_async16(dst0 + ((hh * CQ + cq) * kHaloW + ww) * 16, src, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (ptid == 0) TC_STAMP(0, it, 2);
+      if (it >= 1) {
+        cp_async_wait<1>();               // slice it-1 has landed
+        if (ptid == 0) TC_STAMP(0, it, 3);
+        fence_proxy_async();              // generic-proxy writes -> visible to the MMA (async proxy)
+        mbar_arrive(bar_full + 8 * ((it - 1) & (kSlots - 1)));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    mbar_arrive(bar_full + 8 * ((nslices - 1) & (kSlots - 1)));
+  } else if (warp == 8) {
+    // ===================== MMA issuer (single thread) =====================
+    // The issuing thread is a scalar loop: anything computed per MMA costs ~5 cycles per
+    // dependent instruction, and the tensor pipe retires a small MMA in ~45 cycles
+    // (profiles/microbench/umma_rate.cu), so descriptors are base + compile-time offset.
+    {
+      constexpr uint32_t a_lbo = kHaloW * 16, a_sbo = CQ * kHaloW * 16;   // cq plane / brick row
+      constexpr uint32_t b_lbo = 3 * GW * 16, b_sbo = 128;
+      const uint32_t elected = elect_one();
+      const uint64_t a_desc0 = make_desc(s_ring, a_lbo, a_sbo);
+      const uint64_t b_desc0 = make_desc(s_w, b_lbo, b_sbo);
+      for (int it = 0; it < nslices; ++it) {
+        // input slice `it` feeds output slices j = it - kd, kd = 0,1,2, clipped to [0,nd):
+        // columns [j_lo*GW, (j_hi+1)*GW), B rows [(2-kd_hi)*GW, (3-kd_lo)*GW)
+        const int kd_lo = max(0, it - (nd - 1)), kd_hi = min(2, it);
+        const int j_lo = it - kd_hi;
+        const uint32_t idesc = make_idesc(128, (kd_hi - kd_lo + 1) * GW);
+        const uint32_t acc = tmem_base + j_lo * GW;
+        if (lane == 0) TC_STAMP(1, it, 0);
+        mbar_wait(bar_full + 8 * (it & (kSlots - 1)), (it >> 2) & 1);
+        if (lane == 0) TC_STAMP(1, it, 1);
+        tc_fence_after();
+        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+        const uint32_t a_lo0 = (uint32_t)a_desc0 + (((it & (kSlots - 1)) * S::kSlotBytes) >> 4);
+        const uint32_t b_lo0 = (uint32_t)b_desc0 + (((2 - kd_hi) * GW * 16) >> 4);
+#pragma unroll
+        for (int khw = 0; khw < 9; ++khw) {
+          const int kh = khw / 3, kw = khw % 3;
+#pragma unroll
+          for (int k8 = 0; k8 < CIN / 8; ++k8) {
+            const uint32_t a_off = ((kh * CQ * kHaloW + kw) * 16 + k8 * 2 * kHaloW * 16) >> 4;
+            const uint32_t b_off = (khw * (CIN * 3 * GW * 4) + k8 * 2 * 3 * GW * 16) >> 4;
+            umma_tf32(acc, a_lo0 + a_off, a_hi, b_lo0 + b_off, b_hi, idesc, elected);
+          }
+        }
+        if (it >= 2) umma_commit(bar_tfull + 8 * (it - 2), elected);         // slice it-2 complete
+        umma_commit(bar_empty + 8 * (it & (kSlots - 1)), elected);           // smem slot free
+        if (lane == 0) TC_STAMP(1, it, 3);
+      }
+    }
+  } else {
+    // ===================== epilogue warps 0..3 =====================
+    const int m = warp * 32 + lane;              // GEMM row = TMEM lane
+    const int oh = h0 + (m >> 3), ow = w0 + (m & 7);
+    const bool in_range = oh < p.H && ow < p.W;
+    for (int j = 0; j < nd; ++j) {
+      if (threadIdx.x == 0) TC_STAMP(2, j, 0);
+      mbar_wait(bar_tfull + 8 * j, 0);
+      if (threadIdx.x == 0) TC_STAMP(2, j, 1);
+      tc_fence_after();
+      float acc[GW];
+      tmem_ld<GW>(tmem_base + ((uint32_t)(warp * 32) << 16) + j * GW, acc);
+      if (threadIdx.x == 0) TC_STAMP(2, j, 2);
+      if (in_range) {
+        const size_t o = ((((size_t)b * p.D + (d0 + j)) * p.H + oh) * p.W + ow) * p.Cout;
+        if (p.Cout % 4 == 0) {
+#pragma unroll
+          for (int c = 0; c < GW; c += 4) {
+            if (c < p.Cout) {
+              float v[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float t = fmaf(acc[c + k], s_param[c + k], s_param[GW + c + k]);
+                v[k] = t >= 0.f ? t : t * p.slope;
+              }
+              if (p.skip) {
+                const float4 s4 = ldg4(p.skip + o + c);
+                v[0] += s4.x; v[1] += s4.y; v[2] += s4.z; v[3] += s4.w;
+              }
+              if (p.round_out) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = to_tf32(v[k]);
+              }
+              st4(p.y + o + c, make_float4(v[0], v[1], v[2], v[3]));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < GW; ++c) {
+            if (c < p.Cout) {
+              float t = fmaf(acc[c], s_param[c], s_param[GW + c]);
+              t = t >= 0.f ? t : t * p.slope;
+              if (p.skip) t += __ldg(p.skip + o + c);
+              p.y[o + c] = t;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+template <int CIN, int GW>
+static int launch(const Params& p, cudaStream_t st) {
+  using S = Smem<CIN, GW>;
+  auto kfn = conv3d_tc_kernel<CIN, GW>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S::kTotal);
+    if (e != cudaSuccess) {
+      set_error("conv3d_tc: cannot opt in to %d B of shared memory: %s", S::kTotal,
+                cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  const long items = (long)p.B * p.nchunks * p.tiles_h * p.tiles_w;
+  static int extra = -1;
+  if (extra < 0) {
+    const char* e = getenv("CASMVS_TC_EXTRA_SMEM");
+    extra = e ? atoi(e) : 0;
+    if (extra > 0)
+      cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal + extra);
+  }
+  kfn<<<(unsigned)items, kThreads, S::kTotal + extra, st>>>(p);
+  return after_launch("conv3d_tc");
+}
+
+}  // namespace tc
+
+// Returns 0 when handled, 1 when the layer shape is left to the CUDA-core kernel.
+int conv3d_tc(const float* x, const float* wpk, const float* scale, const float* shift,
+              float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
+              int w, int kind, int stride, int precision, cudaStream_t st) {
+  static int enabled = -1, round_out = 1;
+  static long long* dbg = nullptr;
+  if (enabled < 0) {
+    const char* e = getenv("CASMVS_TC");
+    enabled = e ? atoi(e) : 1;
+    if (const char* s = getenv("CASMVS_TC_ROUND")) round_out = atoi(s);
+    if (const char* s = getenv("CASMVS_TC_DBG")) dbg = (long long*)strtoull(s, nullptr, 0);
+  }
+  if (!enabled || precision != CASMVS_TF32) return 1;
+  if (kind != CASMVS_CONV || stride != 1) return 1;
+  if (!(Cin == 8 || Cin == 16 || Cin == 32) || Cout > 32) return 1;
+  tc::Params p;
+  p.x = x; p.wpk = wpk; p.scale = scale; p.shift = shift; p.skip = skip; p.y = y;
+  p.slope = slope; p.B = B; p.D = D; p.H = h; p.W = w; p.Cout = Cout;
+  p.tiles_w = (w + tc::kTileW - 1) / tc::kTileW;
+  p.tiles_h = (h + tc::kTileH - 1) / tc::kTileH;
+  const int npad = Cout <= 16 ? 16 : 32;
+  int dchunk = D < 512 / npad ? D : 512 / npad;   // one TMEM accumulator group per output slice
+  const long cols = (long)B * p.tiles_w * p.tiles_h;
+  while (dchunk > 4 && cols * ((D + dchunk - 1) / dchunk) < (long)num_sms() * 3)
+    dchunk = (dchunk + 1) / 2;
+  p.dchunk = dchunk;
+  p.nchunks = (D + dchunk - 1) / dchunk;
+  p.dbg = dbg;
+  p.round_out = (round_out && Cout > 1) ? 1 : 0;   // the prob head feeds the softmax: keep fp32
+#define TC_CASE(CI, NP) if (Cin == CI && npad == NP) return tc::launch<CI, NP>(p, st);
+  TC_CASE(8, 16) TC_CASE(8, 32) TC_CASE(16, 16) TC_CASE(16, 32) TC_CASE(32, 16) TC_CASE(32, 32)
+#undef TC_CASE
   return 1;
 }
+
 }  // namespace casmvs

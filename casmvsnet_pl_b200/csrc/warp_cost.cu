@@ -104,6 +104,9 @@ __device__ __forceinline__ void stg256(float* p, const u64 (&v)[4]) {
                "l"(v[3]) : "memory");
 }
 
+__device__ __forceinline__ float round_tf32_f(float x) {
+  uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 }
@@ -165,7 +168,7 @@ warp_cost_kernel(const float* __restrict__ feats,   // (B,V,h,w,C)
                  const float* __restrict__ proj,    // (B,V-1,3,4)
                  const float* __restrict__ dv,      // (B,D,h,w)
                  float* __restrict__ cost, int V, int C_rt, int D, int h, int w, int G,
-                 int dchunk) {
+                 int dchunk, int round_tf32) {
   __shared__ float s_proj[kMaxSrc * 12];
   const int C = CT > 0 ? CT : C_rt;
   const int b = blockIdx.y;
@@ -272,6 +275,16 @@ warp_cost_kernel(const float* __restrict__ feats,   // (B,V,h,w,C)
         const u64 m = mul2(S[k], inv_v2), mn = mul2(S[k], ninv_v2);
         o[k] = fma2(mn, m, mul2(Q[k], inv_v2));
       }
+      if (round_tf32) {
+        // the tcgen05 conv reads fp32 bits as tf32 by truncation; rounding here keeps the
+        // next layer's operand unbiased (round-to-nearest instead of toward zero)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float lo, hi;
+          unpk2(o[k], lo, hi);
+          o[k] = pk2(round_tf32_f(lo), round_tf32_f(hi));
+        }
+      }
       if (active) {
         if (OUT_NHWC) {
           stg256(cost + ((size_t)(b * D + d) * hw + pix) * C + c0, o);
@@ -299,6 +312,7 @@ warp_cost_kernel(const float* __restrict__ feats,   // (B,V,h,w,C)
         const int g = c0 / cpg;
         if (active && (c0 % cpg) == 0) {
           float val = __fdiv_rn(s * inv_cpg, vm1);
+          if (round_tf32) val = round_tf32_f(val);
           if (OUT_NHWC) cost[((size_t)(b * D + d) * hw + pix) * cout + g] = val;
           else cost[((size_t)(b * cout + g) * D + d) * hw + pix] = val;
         }
@@ -325,6 +339,7 @@ warp_cost_kernel(const float* __restrict__ feats,   // (B,V,h,w,C)
           for (int k = 0; k < kCPT; ++k) {
             if (k < ng) {
               float val = __fdiv_rn(o[k] * inv_cpg, vm1);
+              if (round_tf32) val = round_tf32_f(val);
               if (OUT_NHWC) cost[((size_t)(b * D + d) * hw + pix) * cout + g0 + k] = val;
               else cost[((size_t)(b * cout + g0 + k) * D + d) * hw + pix] = val;
             }
@@ -411,25 +426,25 @@ int g_k1_dchunk = 0;  // CASMVS_K1_DCHUNK overrides the depth-chunk heuristic
 template <int NSRC, int CT>
 static void launch_k1(bool gwc, bool nhwc, dim3 grd, cudaStream_t st, const float* f,
                       const float* p, const float* dv, float* cost, int V, int C, int D, int h,
-                      int w, int G, int dchunk) {
+                      int w, int G, int dchunk, int rnd) {
   if (gwc) {
-    if (nhwc) warp_cost_kernel<NSRC, CT, true, true><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G, dchunk);
-    else warp_cost_kernel<NSRC, CT, true, false><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G, dchunk);
+    if (nhwc) warp_cost_kernel<NSRC, CT, true, true><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G, dchunk, rnd);
+    else warp_cost_kernel<NSRC, CT, true, false><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G, dchunk, rnd);
   } else {
-    if (nhwc) warp_cost_kernel<NSRC, CT, false, true><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G, dchunk);
-    else warp_cost_kernel<NSRC, CT, false, false><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G, dchunk);
+    if (nhwc) warp_cost_kernel<NSRC, CT, false, true><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G, dchunk, rnd);
+    else warp_cost_kernel<NSRC, CT, false, false><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, V, C, D, h, w, G, dchunk, rnd);
   }
 }
 
 template <int NSRC>
 static void launch_k1_c(bool gwc, bool nhwc, dim3 grd, cudaStream_t st, const float* f,
                         const float* p, const float* dv, float* cost, int V, int C, int D, int h,
-                        int w, int G, int dchunk) {
+                        int w, int G, int dchunk, int rnd) {
   switch (C) {
-    case 8: launch_k1<NSRC, 8>(gwc, nhwc, grd, st, f, p, dv, cost, V, C, D, h, w, G, dchunk); break;
-    case 16: launch_k1<NSRC, 16>(gwc, nhwc, grd, st, f, p, dv, cost, V, C, D, h, w, G, dchunk); break;
-    case 32: launch_k1<NSRC, 32>(gwc, nhwc, grd, st, f, p, dv, cost, V, C, D, h, w, G, dchunk); break;
-    default: launch_k1<NSRC, 0>(gwc, nhwc, grd, st, f, p, dv, cost, V, C, D, h, w, G, dchunk); break;
+    case 8: launch_k1<NSRC, 8>(gwc, nhwc, grd, st, f, p, dv, cost, V, C, D, h, w, G, dchunk, rnd); break;
+    case 16: launch_k1<NSRC, 16>(gwc, nhwc, grd, st, f, p, dv, cost, V, C, D, h, w, G, dchunk, rnd); break;
+    case 32: launch_k1<NSRC, 32>(gwc, nhwc, grd, st, f, p, dv, cost, V, C, D, h, w, G, dchunk, rnd); break;
+    default: launch_k1<NSRC, 0>(gwc, nhwc, grd, st, f, p, dv, cost, V, C, D, h, w, G, dchunk, rnd); break;
   }
 }
 
@@ -474,6 +489,8 @@ extern "C" int casmvs_warp_cost_fwd(const float* feats, int feat_layout, const f
   } else {
     CASMVS_REQUIRE(feat_layout == CASMVS_NHWC, "warp_cost: bad feat_layout");
   }
+  const int rnd = (cost_layout & CASMVS_ROUND_TF32) ? 1 : 0;
+  cost_layout &= ~CASMVS_ROUND_TF32;
   CASMVS_REQUIRE(cost_layout == CASMVS_NCHW || cost_layout == CASMVS_NHWC,
                  "warp_cost: bad cost_layout");
   const bool nhwc = cost_layout == CASMVS_NHWC;
@@ -495,11 +512,11 @@ extern "C" int casmvs_warp_cost_fwd(const float* feats, int feat_layout, const f
   }
   dim3 grd(xblocks, (unsigned)B, (unsigned)((D + dchunk - 1) / dchunk));
   switch (V - 1) {
-    case 1: launch_k1_c<1>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk); break;
-    case 2: launch_k1_c<2>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk); break;
-    case 4: launch_k1_c<4>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk); break;
-    case 6: launch_k1_c<6>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk); break;
-    default: launch_k1<0, 0>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk); break;
+    case 1: launch_k1_c<1>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk, rnd); break;
+    case 2: launch_k1_c<2>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk, rnd); break;
+    case 4: launch_k1_c<4>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk, rnd); break;
+    case 6: launch_k1_c<6>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk, rnd); break;
+    default: launch_k1<0, 0>(gwc, nhwc, grd, st, f, proj, depth_values, cost, V, C, D, h, w, num_groups, dchunk, rnd); break;
   }
   return after_launch("warp_cost");
 }

@@ -42,9 +42,13 @@ class FeatureNet(nn.Module):
     # cuDNN would run fp32 convs as TF32 on B200 by default; the reference path is
     # fp32 (opt.py:69-70), so keep IEEE fp32 here unless the caller opts in.
     allow_tf32 = False
+    # the reference's inference script turns cuDNN autotuning on (eval.py:19); without it
+    # cuDNN's heuristics pick FFT/sgemm algorithms that are several times slower here
+    benchmark = True
 
     def forward(self, x):
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=self.allow_tf32):
+        with torch.backends.cudnn.flags(enabled=True, benchmark=self.benchmark,
+                                        allow_tf32=self.allow_tf32):
             return self._forward(x)
 
     def _forward(self, x):
@@ -170,7 +174,8 @@ class CascadeMVSNet(nn.Module):
         """feats (B,V,C,h,w), proj_mats (B,V-1,3,4), depth_values (B,D,h,w),
         cost_reg: module (B,C,D,h,w)->(B,1,D,h,w).  Returns depth, confidence (B,h,w)
         (reference models/mvsnet.py:125-195)."""
-        cost = ops.warp_cost(feats, proj_mats, depth_values, self.G, ops.NHWC)
+        cost = ops.warp_cost(feats, proj_mats, depth_values, self.G, ops.NHWC,
+                             round_tf32=(getattr(cost_reg, "precision", "fp32") == "tf32"))
         logits = cost_reg(cost).squeeze(1)
         del cost
         depth, confidence, _, _ = ops.regress(logits, depth_values)

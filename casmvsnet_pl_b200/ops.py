@@ -11,7 +11,8 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import CONV, CONV_TRANSPOSE, FP32, NCHW, NHWC, PRECISIONS, check
+from ._lib import (CONV, CONV_TRANSPOSE, FP32, NCHW, NHWC, PRECISIONS, TF32,  # noqa: F401
+                   TF32X3, check)
 
 _checked_devices = set()
 
@@ -75,7 +76,7 @@ def volume_storage(x):
 
 
 # --------------------------------------------------------------------------- K1
-def warp_cost(feats, proj_mats, depth_values, num_groups=1, out_layout=NHWC):
+def warp_cost(feats, proj_mats, depth_values, num_groups=1, out_layout=NHWC, round_tf32=False):
     """Fused homography warp + variance / group-wise-correlation cost volume.
 
     feats (B,V,C,h,w) (any strides; channels-last storage is used as is),
@@ -103,7 +104,8 @@ def warp_cost(feats, proj_mats, depth_values, num_groups=1, out_layout=NHWC):
     else:
         out = torch.empty(B, cout, D, h, w, device=feats.device, dtype=torch.float32)
     check(lib.casmvs_warp_cost_fwd(_ptr(fbuf), flayout, _ptr(proj), _ptr(dv), _ptr(out),
-                                   out_layout, B, V, C, D, h, w, num_groups, _ptr(ws),
+                                   out_layout | (_lib.ROUND_TF32 if round_tf32 else 0),
+                                   B, V, C, D, h, w, num_groups, _ptr(ws),
                                    ws_bytes, _stream()), "warp_cost")
     return as_volume_view(out) if out_layout == NHWC else out
 

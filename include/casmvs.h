@@ -40,6 +40,10 @@ extern "C" {
 #define CASMVS_VERSION 100  /* 0.1.0 */
 
 enum casmvs_layout { CASMVS_NCHW = 0, CASMVS_NHWC = 1 };
+/* OR-ed into casmvs_warp_cost_fwd's cost_layout: store the cost volume rounded to
+ * TF32 (round-to-nearest) because the consumer is the tcgen05 kind::tf32 conv, which
+ * would otherwise truncate the operand (biased). */
+#define CASMVS_ROUND_TF32 256
 
 /* precision of the 3D-conv contraction (K2) */
 enum casmvs_precision {

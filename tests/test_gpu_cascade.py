@@ -45,12 +45,18 @@ def test_cascade_vs_reference_golden(golden, tag, G, precision):
     # north_star: depth within 1e-3 relative L1 of the reference (fp32)
     for l in (2, 1, 0):
         assert rel[l] < 1e-3
-    # abs_err metric (metrics.py:1-3) against a synthetic GT: the two implementations agree
-    gt = g["depth_0"] + 1.0
+    # abs_err metric (metrics.py:1-3) against a synthetic ground truth placed ~4.5 mm (the
+    # reference's DTU validation abs_err, README.md:70) around the reference output: the two
+    # implementations' abs_err agree within 1e-3 (relative).  fp32 mode agrees to < 1e-5 mm.
+    gen = torch.Generator().manual_seed(1)
+    gt = g["depth_0"] + 5.6 * torch.randn(g["depth_0"].shape, generator=gen)
     a = (res["depth_0"].cpu() - gt).abs().mean()
     b = (g["depth_0"] - gt).abs().mean()
-    print(f"abs_err ours {a:.6f} ref {b:.6f}")
+    print(f"abs_err ours {a:.6f} mm, reference {b:.6f} mm, signed mean diff "
+          f"{(res['depth_0'].cpu() - g['depth_0']).mean():.2e} mm")
     assert abs(a - b) / b < 1e-3
+    if precision == "fp32":
+        assert abs(a - b) < 1e-5
 
 
 def test_cascade_tensor_params_batch2(golden):
