@@ -1,0 +1,71 @@
+"""Data-parallel depth inference over the GPUs of one box.
+
+Reference views are independent (eval.py:213-222 has no cross-iteration state and
+eval-mode BN has no cross-batch ops), so the batch of reference views is sharded
+over ranks with NO collective on the data path; the only exchange is ONE all_gather
+of the per-view results at the end (depth_0 and the confidence_2 map eval.py:224-226
+consumes).  One process per GPU (torchrun), NCCL on GPUs, gloo for the CPU tests of
+this host logic.  Results are bit-identical to a single-rank run (no reduction).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, rank: int, world: int):
+    """Contiguous, balanced split: the first n % world ranks get one extra item."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def max_shard(n_items: int, world: int) -> int:
+    return -(-n_items // world)
+
+
+def sharded_depth_inference(engine, imgs, proj_mats, init_depth_min, depth_interval,
+                            keys=("depth_0", "confidence_2"), group=None):
+    """Run `engine(imgs, proj_mats, init_depth_min, depth_interval) -> dict` on this
+    rank's shard of the reference views and all_gather the requested outputs.
+
+    imgs (B,V,3,H,W), proj_mats (B,V-1,3,3,4) hold ALL B reference views on every rank
+    (or at least this rank's shard rows; only those are touched).  init_depth_min /
+    depth_interval: float or (B,1) tensors.  Returns {key: (B,h,w)} on every rank.
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = imgs.shape[0]
+    lo, hi = shard_bounds(B, rank, world)
+
+    def pick(x):
+        return x[lo:hi] if torch.is_tensor(x) else x
+
+    if hi > lo:
+        local = engine(imgs[lo:hi], proj_mats[lo:hi], pick(init_depth_min), pick(depth_interval))
+    else:
+        local = None
+    if world == 1:
+        return {k: local[k] for k in keys}
+
+    # every rank must know the output shapes even if its shard is empty
+    cap = max_shard(B, world)
+    shapes = torch.zeros(len(keys), 2, dtype=torch.int64, device=imgs.device)
+    if local is not None:
+        for i, k in enumerate(keys):
+            shapes[i, 0], shapes[i, 1] = local[k].shape[-2:]
+    dist.all_reduce(shapes, op=dist.ReduceOp.MAX, group=group)
+    out = {}
+    for i, k in enumerate(keys):
+        h, w = int(shapes[i, 0]), int(shapes[i, 1])
+        send = torch.zeros(cap, h, w, dtype=torch.float32, device=imgs.device)
+        if local is not None:
+            send[: hi - lo] = local[k]
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(recv, send, group=group)          # the path's single collective
+        parts = []
+        for r in range(world):
+            rlo, rhi = shard_bounds(B, r, world)
+            parts.append(recv[r][: rhi - rlo])
+        out[k] = torch.cat(parts, 0)
+    return out
