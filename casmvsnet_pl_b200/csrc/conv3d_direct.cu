@@ -232,7 +232,13 @@ int conv3d_direct(const float* x, const float* wpk, const float* scale, const fl
   dm.B = B; dm.Cin = Cin; dm.Cout = Cout; dm.Di = D; dm.hi = h; dm.wi = w;
   if (kind == CASMVS_CONV) {
     dm.Do = (D - 1) / stride + 1; dm.ho = (h - 1) / stride + 1; dm.wo = (w - 1) / stride + 1;
-    if (stride == 1) return launch_direct<K_CONV_S1, 4>(x, wpk, scale, shift, slope, skip, y, dm, st, round_out);
+    if (stride == 1) {
+      // small (deep) volumes: one voxel per thread so that the grid still covers the SMs
+      const long groups4 = (long)B * dm.Do * dm.ho * ((dm.wo + 3) / 4) * ((Cout + 7) / 8);
+      if (groups4 < (long)num_sms() * kConvThreads * 2)
+        return launch_direct<K_CONV_S1, 1>(x, wpk, scale, shift, slope, skip, y, dm, st, round_out);
+      return launch_direct<K_CONV_S1, 4>(x, wpk, scale, shift, slope, skip, y, dm, st, round_out);
+    }
     return launch_direct<K_CONV_S2, 1>(x, wpk, scale, shift, slope, skip, y, dm, st, round_out);
   }
   dm.Do = 2 * D; dm.ho = 2 * h; dm.wo = 2 * w;

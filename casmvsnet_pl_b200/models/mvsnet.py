@@ -39,8 +39,8 @@ class FeatureNet(nn.Module):
     def _up2(x):
         return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=True)
 
-    # cuDNN would run fp32 convs as TF32 on B200 by default; the reference path is
-    # fp32 (opt.py:69-70), so keep IEEE fp32 here unless the caller opts in.
+    # cuDNN would run fp32 convs as TF32 on B200 by default; the reference path is fp32
+    # (opt.py:69-70), so IEEE fp32 is kept unless the model runs in its tf32 precision mode.
     allow_tf32 = False
     # the reference's inference script turns cuDNN autotuning on (eval.py:19); without it
     # cuDNN's heuristics pick FFT/sgemm algorithms that are several times slower here
@@ -49,14 +49,50 @@ class FeatureNet(nn.Module):
     def forward(self, x):
         with torch.backends.cudnn.flags(enabled=True, benchmark=self.benchmark,
                                         allow_tf32=self.allow_tf32):
-            return self._forward(x)
+            if self.training or torch.is_grad_enabled():
+                return self._forward_modules(x)
+            return self._forward_folded(x)
 
-    def _forward(self, x):
+    # -- inference path: eval-mode ABN folded into the conv (w*alpha, beta') so each block
+    #    is one cuDNN conv with bias + an in-place LeakyReLU instead of conv + BN + act
+    def _folded(self):
+        from ..norm_act import activation_slope, folded_scale_shift
+        blocks = [m for seq in (self.conv0, self.conv1, self.conv2) for m in seq]
+        key = tuple((t.data_ptr(), t._version) for b in blocks for t in
+                    (b.conv.weight, b.bn.weight, b.bn.bias, b.bn.running_mean, b.bn.running_var))
+        if getattr(self, "_fold_key", None) != key:
+            cache = []
+            for b in blocks:
+                a, beta = folded_scale_shift(b.bn)
+                w = (b.conv.weight.detach() * a.reshape(-1, 1, 1, 1)).contiguous(
+                    memory_format=torch.channels_last)
+                cache.append((w, beta.contiguous(), b.conv.stride, b.conv.padding,
+                              activation_slope(b.bn)))
+            self._fold_cache, self._fold_key = cache, key
+        return self._fold_cache
+
+    def _forward_folded(self, x):
+        x = x.contiguous(memory_format=torch.channels_last)
+        cache = self._folded()
+
+        def run(t, lo, hi):
+            for w, b, stride, pad, slope in cache[lo:hi]:
+                t = F.leaky_relu_(F.conv2d(t, w, b, stride, pad), slope)
+            return t
+        c0 = run(x, 0, 2)
+        c1 = run(c0, 2, 5)
+        c2 = run(c1, 5, 8)
+        return self._head(c0, c1, c2)
+
+    def _forward_modules(self, x):
         # channels-last end to end: level_l come out physically (N,h,w,C)
         x = x.contiguous(memory_format=torch.channels_last)
         c0 = self.conv0(x)
         c1 = self.conv1(c0)
         c2 = self.conv2(c1)
+        return self._head(c0, c1, c2)
+
+    def _head(self, c0, c1, c2):
         f2 = self.toplayer(c2)
         f1 = self._up2(f2) + self.lat1(c1)
         f0 = self._up2(f1) + self.lat0(c0)
@@ -168,6 +204,8 @@ class CascadeMVSNet(nn.Module):
         for m in self.modules():
             if isinstance(m, (CostRegNet, ConvBnReLU3D)):
                 m.precision = precision
+        # in tf32 mode the 2D FeatureNet convs may use cuDNN's TF32 tensor-core kernels too
+        self.feature.allow_tf32 = precision == "tf32"
         return self
 
     def predict_depth(self, feats, proj_mats, depth_values, cost_reg):
