@@ -39,12 +39,14 @@ namespace tc {
 struct Params {
   const float* x;       // (B,D,H,W,CIN)
   const float* wpk;     // [27][CIN][Cout]  (direct-kernel packing)
+  const float* bimg;    // pre-built B operand image [kh][kw][CIN/4][3*GW][4] (tf32-rounded)
   const float* scale;   // [Cout] or null
   const float* shift;   // [Cout] or null
   const float* skip;    // (B,D,H,W,Cout) or null
   float* y;             // (B,D,H,W,Cout)
   float slope;
-  int B, D, H, W, Cout;
+  int B, D, H, W, Cout;   // Cout = channels handled by one CTA (<= GW)
+  int cout_total;         // channel count of the output tensor; blockIdx.y selects the chunk
   int tiles_w, tiles_h, nchunks, dchunk;
   int round_out;        // round the stored activations to tf32 (unbiased next-layer operand)
   long long* dbg;       // optional timeline of CTA 0: [role][slice][4] clock64 stamps
@@ -57,10 +59,12 @@ struct Params {
 template <int CIN, int GW>
 struct Smem {
   static constexpr int CQ = CIN / 4;
+  // 64-channel (deep) layers: one CTA handles a 16-channel slice of Cout with a 2-slot ring
+  static constexpr int SLOTS = CIN > 32 ? 2 : 4;
   static constexpr int kSlotBytes = kHaloH * CQ * kHaloW * 16;
   static constexpr int kWBytes = 9 * CIN * 3 * GW * 4;               // [kh][kw][cq][3*GW][4]
   static constexpr int kRingOff = kWBytes;
-  static constexpr int kParamOff = kRingOff + kSlots * kSlotBytes;   // scale/shift [2][GW]
+  static constexpr int kParamOff = kRingOff + SLOTS * kSlotBytes;   // scale/shift [2][GW]
   static constexpr int kBarOff = kParamOff + 2 * GW * 4;
   static constexpr int kTotal = kBarOff + 128 + 32 * 8;
 };
@@ -74,6 +78,7 @@ template <int CIN, int GW>
 __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) {
   using S = Smem<CIN, GW>;
   constexpr int CQ = S::CQ;
+  constexpr int SLOTS = S::SLOTS;
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_w = s_base, s_ring = s_base + S::kRingOff, s_bar = s_base + S::kBarOff;
@@ -102,7 +107,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) 
   // ---- one-time setup ----
   if (threadIdx.x == 0) TC_STAMP(3, 0, 0);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSlots; ++i) {
+    for (int i = 0; i < SLOTS; ++i) {
       mbar_init(bar_full + 8 * i, kProducerThreads);
       mbar_init(bar_empty + 8 * i, 1);
     }
@@ -110,24 +115,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) 
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(smem_u32((const void*)s_tmem_ptr), tmem_cols);
-  // weights -> smem as the B operand image [kh][kw][cq][n = g*GW + co][4], g = 2 - kd,
-  // tf32-rounded (round to nearest), zero rows for co >= Cout
-  for (int i = threadIdx.x; i < 9 * CIN * 3 * GW; i += kThreads) {
-    const int j = i & 3;
-    const int n = (i >> 2) % (3 * GW);
-    const int r = (i >> 2) / (3 * GW);    // (kh*3+kw)*CQ + cq
-    const int cq = r % CQ, khw = r / CQ;
-    const int g = n / GW, co = n % GW;
-    const int kd = 2 - g;
-    const int ci = cq * 4 + j;
-    float v = 0.f;
-    if (co < p.Cout)
-      v = to_tf32(__ldg(p.wpk + ((size_t)(kd * 9 + khw) * CIN + ci) * p.Cout + co));
-    reinterpret_cast<float*>(smem)[i] = v;
-  }
+  // B operand image (built once per launch by build_image_kernel) -> smem
+  const int co_base = blockIdx.y * p.Cout;
+  load_image_async(s_w, p.bimg + (size_t)blockIdx.y * (S::kWBytes / 4), S::kWBytes);
   for (int i = threadIdx.x; i < GW; i += kThreads) {
-    s_param[i] = (i < p.Cout) ? (p.scale ? __ldg(p.scale + i) : 1.f) : 0.f;
-    s_param[GW + i] = (i < p.Cout) ? (p.shift ? __ldg(p.shift + i) : 0.f) : 0.f;
+    s_param[i] = (i < p.Cout) ? (p.scale ? __ldg(p.scale + co_base + i) : 1.f) : 0.f;
+    s_param[GW + i] = (i < p.Cout) ? (p.shift ? __ldg(p.shift + co_base + i) : 0.f) : 0.f;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -153,9 +146,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) 
     const int ptid = threadIdx.x - 128;
     for (int it = 0; it < nslices; ++it) {
       const int s = d0 - 1 + it;
-      const int slot = it & (kSlots - 1);
+      const int slot = it % SLOTS;
       if (ptid == 0) TC_STAMP(0, it, 0);
-      if (it >= kSlots) mbar_wait(bar_empty + 8 * slot, ((it >> 2) - 1) & 1);
+      if (it >= SLOTS) mbar_wait(bar_empty + 8 * slot, ((it / SLOTS) - 1) & 1);
       if (ptid == 0) TC_STAMP(0, it, 1);
       const uint32_t dst0 = s_ring + slot * S::kSlotBytes;
       const bool s_ok = (s >= 0) && (s < p.D);
@@ -175,12 +168,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) 
         cp_async_wait<1>();               // slice it-1 has landed
         if (ptid == 0) TC_STAMP(0, it, 3);
         fence_proxy_async();              // generic-proxy writes -> visible to the MMA (async proxy)
-        mbar_arrive(bar_full + 8 * ((it - 1) & (kSlots - 1)));
+        mbar_arrive(bar_full + 8 * ((it - 1) % SLOTS));
       }
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    mbar_arrive(bar_full + 8 * ((nslices - 1) & (kSlots - 1)));
+    mbar_arrive(bar_full + 8 * ((nslices - 1) % SLOTS));
   } else if (warp == 8) {
     // ===================== MMA issuer (single thread) =====================
     // The issuing thread is a scalar loop: anything computed per MMA costs ~5 cycles per
@@ -200,11 +193,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) 
         const uint32_t idesc = make_idesc(128, (kd_hi - kd_lo + 1) * GW);
         const uint32_t acc = tmem_base + j_lo * GW;
         if (lane == 0) TC_STAMP(1, it, 0);
-        mbar_wait(bar_full + 8 * (it & (kSlots - 1)), (it >> 2) & 1);
+        mbar_wait(bar_full + 8 * (it % SLOTS), (it / SLOTS) & 1);
         if (lane == 0) TC_STAMP(1, it, 1);
         tc_fence_after();
         const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
-        const uint32_t a_lo0 = (uint32_t)a_desc0 + (((it & (kSlots - 1)) * S::kSlotBytes) >> 4);
+        const uint32_t a_lo0 = (uint32_t)a_desc0 + (((it % SLOTS) * S::kSlotBytes) >> 4);
         const uint32_t b_lo0 = (uint32_t)b_desc0 + (((2 - kd_hi) * GW * 16) >> 4);
 #pragma unroll
         for (int khw = 0; khw < 9; ++khw) {
@@ -217,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) 
           }
         }
         if (it >= 2) umma_commit(bar_tfull + 8 * (it - 2), elected);         // slice it-2 complete
-        umma_commit(bar_empty + 8 * (it & (kSlots - 1)), elected);           // smem slot free
+        umma_commit(bar_empty + 8 * (it % SLOTS), elected);                  // smem slot free
         if (lane == 0) TC_STAMP(1, it, 3);
       }
     }
@@ -235,7 +228,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) 
       tmem_ld<GW>(tmem_base + ((uint32_t)(warp * 32) << 16) + j * GW, acc);
       if (threadIdx.x == 0) TC_STAMP(2, j, 2);
       if (in_range) {
-        const size_t o = ((((size_t)b * p.D + (d0 + j)) * p.H + oh) * p.W + ow) * p.Cout;
+        const size_t o =
+            ((((size_t)b * p.D + (d0 + j)) * p.H + oh) * p.W + ow) * p.cout_total + co_base;
         if (p.Cout % 4 == 0) {
 #pragma unroll
           for (int c = 0; c < GW; c += 4) {
@@ -280,8 +274,45 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) 
   }
 }
 
+// [kh][kw][cq][n = g*GW + co][4], g = 2 - kd; tf32-rounded (to nearest); zero rows for co >= Cout
+// One image per Cout chunk (chunk = blockIdx.y of the conv kernel), `chunk` channels each.
+__global__ void build_image_kernel(const float* __restrict__ wpk, float* __restrict__ img,
+                                   int CIN, int GW, int chunk, int cout_total) {
+  const int CQ = CIN / 4;
+  const int per = 9 * CIN * 3 * GW;
+  const int total = per * (cout_total / chunk);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int ck = t / per, i = t - ck * per;
+    const int j = i & 3;
+    const int n = (i >> 2) % (3 * GW);
+    const int r = (i >> 2) / (3 * GW);    // (kh*3+kw)*CQ + cq
+    const int cq = r % CQ, khw = r / CQ;
+    const int g = n / GW, co = n % GW;
+    const int kd = 2 - g;
+    const int ci = cq * 4 + j;
+    float v = 0.f;
+    if (co < chunk)
+      v = to_tf32(__ldg(wpk + ((size_t)(kd * 9 + khw) * CIN + ci) * cout_total + ck * chunk + co));
+    img[t] = v;
+  }
+}
+
+float* image_scratch(size_t bytes) {
+  constexpr int kRing = 8;
+  constexpr size_t kSlot = 512 * 1024;
+  static float* base = nullptr;
+  static int next = 0;
+  if (bytes > kSlot) return nullptr;
+  if (!base) {
+    if (cudaMalloc(&base, kRing * kSlot) != cudaSuccess) { base = nullptr; return nullptr; }
+  }
+  float* p = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + (size_t)next * kSlot);
+  next = (next + 1) % kRing;
+  return p;
+}
+
 template <int CIN, int GW>
-static int launch(const Params& p, cudaStream_t st) {
+static int launch(Params p, cudaStream_t st) {
   using S = Smem<CIN, GW>;
   auto kfn = conv3d_tc_kernel<CIN, GW>;
   static bool attr_set = false;
@@ -295,6 +326,22 @@ static int launch(const Params& p, cudaStream_t st) {
     }
     attr_set = true;
   }
+  // depth chunk: one TMEM accumulator group (GW columns) per output slice, and as many
+  // CTAs per SM as shared memory allows must be able to hold their TMEM at once
+  const int per_sm = S::kTotal * 4 <= 227 * 1024 ? 4 : S::kTotal * 2 <= 227 * 1024 ? 2 : 1;
+  const int cap = (512 / per_sm) / GW;
+  int dchunk = p.D < cap ? p.D : cap;
+  const long cols = (long)p.B * p.tiles_w * p.tiles_h;
+  while (dchunk > 4 && cols * ((p.D + dchunk - 1) / dchunk) < (long)num_sms() * 3 * per_sm)
+    dchunk = (dchunk + 1) / 2;
+  p.dchunk = dchunk;
+  p.nchunks = (p.D + dchunk - 1) / dchunk;
+  const int nco = p.cout_total / p.Cout;
+  float* img = image_scratch((size_t)S::kWBytes * nco);
+  if (!img) { set_error("conv3d_tc: cannot allocate the weight-image scratch"); return -2; }
+  build_image_kernel<<<64, 256, 0, st>>>(p.wpk, img, CIN, GW, p.Cout, p.cout_total);
+  if (int rc = after_launch("conv3d_tc/build_image")) return rc;
+  p.bimg = img;
   const long items = (long)p.B * p.nchunks * p.tiles_h * p.tiles_w;
   static int extra = -1;
   if (extra < 0) {
@@ -303,7 +350,7 @@ static int launch(const Params& p, cudaStream_t st) {
     if (extra > 0)
       cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal + extra);
   }
-  kfn<<<(unsigned)items, kThreads, S::kTotal + extra, st>>>(p);
+  kfn<<<dim3((unsigned)items, (unsigned)nco), kThreads, S::kTotal + extra, st>>>(p);
   return after_launch("conv3d_tc");
 }
 
@@ -323,23 +370,20 @@ int conv3d_tc(const float* x, const float* wpk, const float* scale, const float*
   }
   if (!enabled || precision != CASMVS_TF32) return 1;
   if (kind != CASMVS_CONV || stride != 1) return 1;
-  if (!(Cin == 8 || Cin == 16 || Cin == 32) || Cout > 32) return 1;
+  const bool deep = Cin == 64 && Cout == 64;          // conv6: 16-channel Cout slices
+  if (!deep && (!(Cin == 8 || Cin == 16 || Cin == 32) || Cout > 32)) return 1;
   tc::Params p;
   p.x = x; p.wpk = wpk; p.scale = scale; p.shift = shift; p.skip = skip; p.y = y;
-  p.slope = slope; p.B = B; p.D = D; p.H = h; p.W = w; p.Cout = Cout;
+  p.slope = slope; p.B = B; p.D = D; p.H = h; p.W = w;
+  p.Cout = deep ? 16 : Cout; p.cout_total = Cout;
   p.tiles_w = (w + tc::kTileW - 1) / tc::kTileW;
   p.tiles_h = (h + tc::kTileH - 1) / tc::kTileH;
-  const int npad = Cout <= 16 ? 16 : 32;
-  int dchunk = D < 512 / npad ? D : 512 / npad;   // one TMEM accumulator group per output slice
-  const long cols = (long)B * p.tiles_w * p.tiles_h;
-  while (dchunk > 4 && cols * ((D + dchunk - 1) / dchunk) < (long)num_sms() * 3)
-    dchunk = (dchunk + 1) / 2;
-  p.dchunk = dchunk;
-  p.nchunks = (D + dchunk - 1) / dchunk;
+  const int npad = p.Cout <= 16 ? 16 : 32;
   p.dbg = dbg;
   p.round_out = (round_out && Cout > 1) ? 1 : 0;   // the prob head feeds the softmax: keep fp32
 #define TC_CASE(CI, NP) if (Cin == CI && npad == NP) return tc::launch<CI, NP>(p, st);
   TC_CASE(8, 16) TC_CASE(8, 32) TC_CASE(16, 16) TC_CASE(16, 32) TC_CASE(32, 16) TC_CASE(32, 32)
+  TC_CASE(64, 16)
 #undef TC_CASE
   return 1;
 }

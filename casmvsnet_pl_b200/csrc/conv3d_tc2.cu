@@ -36,12 +36,14 @@ enum { MODE_S2 = 0, MODE_T = 1 };
 struct Params {
   const float* x;      // (B,Di,Hi,Wi,CIN)
   const float* wpk;    // [27][CIN][Cout]
+  const float* bimg;   // pre-built B operand image [tap][CIN/4][BROWS][4] (tf32-rounded)
   const float* scale;  // [Cout]
   const float* shift;  // [Cout]
   const float* skip;   // output-shaped or null
   float* y;            // (B,Do,Ho,Wo,Cout)
   float slope;
-  int B, Di, Hi, Wi, Do, Ho, Wo, Cout;
+  int B, Di, Hi, Wi, Do, Ho, Wo, Cout;     // Cout = channel count of the output tensor;
+                                           // a CTA handles the COUT-channel chunk blockIdx.y
   int tiles_w, tiles_h, nchunks, dchunk;   // tiles over the M space (output for S2, input for T)
   int round_out;
 };
@@ -59,7 +61,9 @@ struct Cfg {
   static constexpr int NTAP = MODE == MODE_S2 ? 9 : 4;      // A views per input slice
   static constexpr int kWBytes = NTAP * CIN * BROWS * 4;
   static constexpr int kRingOff = kWBytes;
-  static constexpr int kParamOff = kRingOff + kSlots * kSlotBytes;   // scale/shift [2][COUT pad 32]
+  // deep layers (big bricks): 2-slot ring, one CTA per COUT-channel chunk of the output
+  static constexpr int SLOTS = (kWBytes + 4 * kSlotBytes + 1024 <= 227 * 1024) ? 4 : 2;
+  static constexpr int kParamOff = kRingOff + SLOTS * kSlotBytes;   // scale/shift [2][COUT pad 32]
   static constexpr int kBarOff = kParamOff + 2 * 32 * 4;
   static constexpr int kTotal = kBarOff + 128 + 32 * 8;
   static constexpr int kMaxGroups = 512 / GW;               // TMEM capacity
@@ -73,6 +77,7 @@ template <int MODE, int CIN, int COUT>
 __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p) {
   using C = Cfg<MODE, CIN, COUT>;
   constexpr int CQ = C::CQ, BR = C::BR, BW = C::BW, GW = C::GW, BROWS = C::BROWS;
+  constexpr int SLOTS = C::SLOTS;
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_w = s_base, s_ring = s_base + C::kRingOff, s_bar = s_base + C::kBarOff;
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p)
   const uint32_t tmem_cols = tmem_cols_for2(p.dchunk * GW);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSlots; ++i) {
+    for (int i = 0; i < SLOTS; ++i) {
       mbar_init(bar_full + 8 * i, kProducerThreads);
       mbar_init(bar_empty + 8 * i, 1);
     }
@@ -106,42 +111,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p)
   }
   if (warp == 0) tmem_alloc(smem_u32((const void*)s_tmem_ptr), tmem_cols);
 
-  // ---- B operand image: [tap][cq][row][4], tf32-rounded ----
-  for (int i = threadIdx.x; i < C::NTAP * CIN * BROWS; i += kThreads) {
-    const int jq = i & 3;
-    const int row = (i >> 2) % BROWS;
-    const int r = (i >> 2) / BROWS;          // tap*CQ + cq
-    const int cq = r % CQ, tap = r / CQ;
-    const int ci = cq * 4 + jq;
-    int kd = -1, kh = -1, kw = -1, co = -1;
-    if (MODE == MODE_S2) {
-      // rows [W(kd=1) | W(kd=2) | W(kd=0)], tap = kh*3+kw
-      const int g = row / GW;
-      co = row % GW;
-      kd = g == 0 ? 1 : g == 1 ? 2 : 0;
-      kh = tap / 3; kw = tap % 3;
-      if (co >= COUT) kd = -1;
-    } else {
-      // tap = sh*2+sw; rows: block 0 kd=0 (pd=1), block 1 kd=1 (pd=0), block 2 kd=2 (pd=1);
-      // inside a block: class (ph,pw) = 2*ph+pw, then co
-      const int sh = tap >> 1, sw = tap & 1;
-      const int blk = row / (4 * COUT);
-      const int cls = (row / COUT) & 3;
-      co = row % COUT;
-      const int ph = cls >> 1, pw = cls & 1;
-      kd = blk;
-      kh = sh == 0 ? (ph == 0 ? 1 : 2) : (ph == 1 ? 0 : -1);
-      kw = sw == 0 ? (pw == 0 ? 1 : 2) : (pw == 1 ? 0 : -1);
-      if (kh < 0 || kw < 0) kd = -1;
-    }
-    float v = 0.f;
-    if (kd >= 0)
-      v = to_tf32(__ldg(p.wpk + ((size_t)((kd * 3 + kh) * 3 + kw) * CIN + ci) * p.Cout + co));
-    reinterpret_cast<float*>(smem)[i] = v;
-  }
+  // B operand image (built once per launch by build_image2_kernel) -> smem
+  const int co_base = blockIdx.y * COUT;
+  load_image_async(s_w, p.bimg + (size_t)blockIdx.y * (C::kWBytes / 4), C::kWBytes);
   for (int i = threadIdx.x; i < 32; i += kThreads) {
-    s_param[i] = (i < COUT) ? (p.scale ? __ldg(p.scale + i) : 1.f) : 0.f;
-    s_param[32 + i] = (i < COUT) ? (p.shift ? __ldg(p.shift + i) : 0.f) : 0.f;
+    s_param[i] = (i < COUT) ? (p.scale ? __ldg(p.scale + co_base + i) : 1.f) : 0.f;
+    s_param[32 + i] = (i < COUT) ? (p.shift ? __ldg(p.shift + co_base + i) : 0.f) : 0.f;
   }
   fence_proxy_async();
   tc_fence_before();
@@ -162,8 +137,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p)
     const int ptid = threadIdx.x - 128;
     for (int it = 0; it < nslices; ++it) {
       const int s = s_first + it;
-      const int slot = it & (kSlots - 1);
-      if (it >= kSlots) mbar_wait(bar_empty + 8 * slot, ((it >> 2) - 1) & 1);
+      const int slot = it % SLOTS;
+      if (it >= SLOTS) mbar_wait(bar_empty + 8 * slot, ((it / SLOTS) - 1) & 1);
       const uint32_t dst0 = s_ring + slot * C::kSlotBytes;
       const bool s_ok = (s >= 0) && (s < p.Di);
       const float* xs = p.x + (((size_t)b * p.Di + (s_ok ? s : 0)) * p.Hi) * (size_t)p.Wi * CIN;
@@ -187,12 +162,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p)
       if (it >= 1) {
         cp_async_wait<1>();
         fence_proxy_async();
-        mbar_arrive(bar_full + 8 * ((it - 1) & (kSlots - 1)));
+        mbar_arrive(bar_full + 8 * ((it - 1) % SLOTS));
       }
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    mbar_arrive(bar_full + 8 * ((nslices - 1) & (kSlots - 1)));
+    mbar_arrive(bar_full + 8 * ((nslices - 1) % SLOTS));
   } else if (warp == 8) {
     // ===================== MMA issuer (warp-uniform, elect-predicated) =====================
     constexpr uint32_t a_lbo = BW * 16;
@@ -229,9 +204,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p)
       (void)kd1_slice;
       const uint32_t idesc = make_idesc(128, ncols);
       const uint32_t acc = tmem_base + col;
-      mbar_wait(bar_full + 8 * (it & (kSlots - 1)), (it >> 2) & 1);
+      mbar_wait(bar_full + 8 * (it % SLOTS), (it / SLOTS) & 1);
       tc_fence_after();
-      const uint32_t a_lo0 = (uint32_t)a_desc0 + (((it & (kSlots - 1)) * C::kSlotBytes) >> 4);
+      const uint32_t a_lo0 = (uint32_t)a_desc0 + (((it % SLOTS) * C::kSlotBytes) >> 4);
       const uint32_t b_lo0 = (uint32_t)b_desc0 + ((row0 * 16) >> 4);
 #pragma unroll
       for (int tap = 0; tap < C::NTAP; ++tap) {
@@ -252,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p)
         }
       }
       if (done >= 0) umma_commit(bar_tfull + 8 * done, elected);
-      umma_commit(bar_empty + 8 * (it & (kSlots - 1)), elected);
+      umma_commit(bar_empty + 8 * (it % SLOTS), elected);
     }
   } else {
     // ===================== epilogue warps 0..3 =====================
@@ -266,7 +241,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p)
         float acc[GW];
         tmem_ld<GW>(lane_base + g * GW, acc);
         if (mh < p.Ho && mw < p.Wo) {
-          const size_t o = ((((size_t)b * p.Do + (g0 + g)) * p.Ho + mh) * p.Wo + mw) * COUT;
+          const size_t o =
+              ((((size_t)b * p.Do + (g0 + g)) * p.Ho + mh) * p.Wo + mw) * p.Cout + co_base;
 #pragma unroll
           for (int c = 0; c < COUT; c += 4) {
             float v[4];
@@ -298,7 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p)
             const int pd = cc >> 2, ph = (cc >> 1) & 1, pw = cc & 1;
             const int od = 2 * (g0 + g) + pd, oh = 2 * mh + ph, ow = 2 * mw + pw;
             if (mh < p.Hi && mw < p.Wi) {
-              const size_t o = ((((size_t)b * p.Do + od) * p.Ho + oh) * p.Wo + ow) * COUT;
+              const size_t o =
+                  ((((size_t)b * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.Cout + co_base;
 #pragma unroll
               for (int c = 0; c < COUT; c += 4) {
                 float v[4];
@@ -332,6 +309,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p)
   }
 }
 
+// B operand image [tap][cq][row][4], tf32-rounded; see the header comment for the row order
+template <int MODE, int CIN, int COUT>
+__global__ void build_image2_kernel(const float* __restrict__ wpk, float* __restrict__ img,
+                                    int cout_total) {
+  using C = Cfg<MODE, CIN, COUT>;
+  constexpr int CQ = C::CQ, GW = C::GW, BROWS = C::BROWS;
+  constexpr int per = C::NTAP * CIN * BROWS;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per * (cout_total / COUT);
+       t += gridDim.x * blockDim.x) {
+    const int ck = t / per, i = t - ck * per;
+    const int jq = i & 3;
+    const int row = (i >> 2) % BROWS;
+    const int r = (i >> 2) / BROWS;          // tap*CQ + cq
+    const int cq = r % CQ, tap = r / CQ;
+    const int ci = cq * 4 + jq;
+    int kd = -1, kh = -1, kw = -1, co = -1;
+    if (MODE == MODE_S2) {
+      // rows [W(kd=1) | W(kd=2) | W(kd=0)], tap = kh*3+kw
+      const int g = row / GW;
+      co = row % GW;
+      kd = g == 0 ? 1 : g == 1 ? 2 : 0;
+      kh = tap / 3; kw = tap % 3;
+      if (co >= COUT) kd = -1;
+    } else {
+      // tap = sh*2+sw; rows: block 0 kd=0 (pd=1), block 1 kd=1 (pd=0), block 2 kd=2 (pd=1);
+      // inside a block: class (ph,pw) = 2*ph+pw, then co
+      const int sh = tap >> 1, sw = tap & 1;
+      const int blk = row / (4 * COUT);
+      const int cls = (row / COUT) & 3;
+      co = row % COUT;
+      const int ph = cls >> 1, pw = cls & 1;
+      kd = blk;
+      kh = sh == 0 ? (ph == 0 ? 1 : 2) : (ph == 1 ? 0 : -1);
+      kw = sw == 0 ? (pw == 0 ? 1 : 2) : (pw == 1 ? 0 : -1);
+      if (kh < 0 || kw < 0) kd = -1;
+    }
+    float v = 0.f;
+    if (kd >= 0)
+      v = to_tf32(__ldg(wpk + ((size_t)((kd * 3 + kh) * 3 + kw) * CIN + ci) * cout_total +
+                        ck * COUT + co));
+    img[t] = v;
+  }
+}
+
 template <int MODE, int CIN, int COUT>
 static int launch2(Params p, cudaStream_t st) {
   using C = Cfg<MODE, CIN, COUT>;
@@ -359,7 +380,13 @@ static int launch2(Params p, cudaStream_t st) {
   p.dchunk = dchunk;
   p.nchunks = (Dm + dchunk - 1) / dchunk;
   const long items = cols * p.nchunks;
-  kfn<<<(unsigned)items, kThreads, C::kTotal, st>>>(p);
+  const int nco = p.Cout / COUT;
+  float* img = image_scratch((size_t)C::kWBytes * nco);
+  if (!img) { set_error("conv3d_tc2: cannot allocate the weight-image scratch"); return -2; }
+  build_image2_kernel<MODE, CIN, COUT><<<64, 256, 0, st>>>(p.wpk, img, p.Cout);
+  if (int rc = after_launch("conv3d_tc2/build_image")) return rc;
+  p.bimg = img;
+  kfn<<<dim3((unsigned)items, (unsigned)nco), kThreads, C::kTotal, st>>>(p);
   return after_launch("conv3d_tc2");
 }
 
@@ -383,12 +410,14 @@ int conv3d_tc2(const float* x, const float* wpk, const float* scale, const float
     p.Do = (D - 1) / 2 + 1; p.Ho = (h - 1) / 2 + 1; p.Wo = (w - 1) / 2 + 1;
     if (Cin == 8 && Cout == 16) return tc2::launch2<tc2::MODE_S2, 8, 16>(p, st);
     if (Cin == 16 && Cout == 32) return tc2::launch2<tc2::MODE_S2, 16, 32>(p, st);
+    if (Cin == 32 && Cout == 64) return tc2::launch2<tc2::MODE_S2, 32, 16>(p, st);   // conv5: 4 chunks
     return 1;
   }
   if (kind == CASMVS_CONV_TRANSPOSE) {
     p.Do = 2 * D; p.Ho = 2 * h; p.Wo = 2 * w;
     if (Cin == 16 && Cout == 8) return tc2::launch2<tc2::MODE_T, 16, 8>(p, st);
     if (Cin == 32 && Cout == 16) return tc2::launch2<tc2::MODE_T, 32, 16>(p, st);
+    if (Cin == 64 && Cout == 32) return tc2::launch2<tc2::MODE_T, 64, 8>(p, st);     // conv7: 4 chunks
     return 1;
   }
   return 1;

@@ -163,5 +163,20 @@ __device__ __forceinline__ void tmem_wait_st() {
 }
 
 
+// Cooperative smem fill of the pre-built B operand image (global, 16 B aligned, bytes % 16 == 0)
+__device__ __forceinline__ void load_image_async(uint32_t dst_smem, const float* src, int bytes) {
+  for (int i = threadIdx.x * 16; i < bytes; i += blockDim.x * 16)
+    cp_async16(dst_smem + i, reinterpret_cast<const char*>(src) + i, 16u);
+  cp_async_commit();
+  cp_async_wait<0>();
+}
+
+// Library-owned scratch for the per-launch B operand images (built by a tiny prologue
+// kernel from the caller's packed weights, then read by every CTA with coalesced
+// cp.async instead of a 4-byte gather per CTA).  A ring of slots so that back-to-back
+// layers on one stream never alias; allocated on first use (run one warm-up forward
+// before capturing a CUDA graph).
+float* image_scratch(size_t bytes);
+
 }  // namespace tc
 }  // namespace casmvs

@@ -8,7 +8,9 @@ dev = "cuda:0"
 torch.manual_seed(0)
 cases = [("conv", 8, 16, (4, 16, 16)), ("conv", 8, 16, (8, 32, 40)), ("conv", 16, 32, (6, 20, 24)),
          ("conv", 8, 16, (48, 128, 160)), ("convT", 16, 8, (2, 16, 8)), ("convT", 16, 8, (5, 18, 11)),
-         ("convT", 32, 16, (3, 16, 16)), ("convT", 16, 8, (24, 64, 80)), ("convT", 32, 16, (12, 32, 40))]
+         ("convT", 32, 16, (3, 16, 16)), ("convT", 16, 8, (24, 64, 80)), ("convT", 32, 16, (12, 32, 40)),
+         ("conv", 32, 64, (4, 16, 16)), ("conv", 32, 64, (12, 32, 40)), ("convT", 64, 32, (2, 16, 8)),
+         ("convT", 64, 32, (6, 16, 20)), ("convT", 64, 32, (1, 64, 80))]
 for kind, cin, cout, dims in cases:
     x = torch.randn(1, cin, *dims, device=dev)
     scale = torch.rand(cout, device=dev) + 0.5

@@ -8,7 +8,8 @@ from casmvsnet_pl_b200 import ops
 dev = "cuda:0"
 torch.manual_seed(0)
 cases = [(8, 8, (2, 16, 8)), (8, 8, (4, 16, 8)), (8, 8, (5, 20, 13)), (16, 16, (6, 32, 24)),
-         (32, 8, (8, 32, 40)), (32, 32, (4, 16, 16)), (8, 1, (8, 32, 16)), (16, 8, (48, 128, 160))]
+         (32, 8, (8, 32, 40)), (32, 32, (4, 16, 16)), (8, 1, (8, 32, 16)), (16, 8, (48, 128, 160)),
+         (64, 64, (2, 16, 8)), (64, 64, (6, 16, 20)), (64, 64, (4, 32, 40)), (64, 64, (1, 64, 80))]
 for cin, cout, dims in cases:
     x = torch.randn(1, cin, *dims, device=dev)
     wt = torch.randn(cout, cin, 3, 3, 3, device=dev) * 0.1
