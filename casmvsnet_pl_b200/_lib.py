@@ -30,6 +30,7 @@ SIGNATURES = {
                                      c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "casmvs_packed_conv3d_weight_floats": (c_size_t, [c_int, c_int]),
     "casmvs_pack_conv3d_weights": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "casmvs_invalidate_weight_cache": (c_int, []),
     "casmvs_conv3d_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
                                   c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_void_p]),
@@ -46,6 +47,7 @@ SIGNATURES = {
                                             c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "casmvs_uniform_hypotheses_fwd": (c_int, [c_float, c_float, c_void_p, c_void_p, c_void_p,
                                               c_int, c_int, c_int, c_int, c_void_p]),
+    "casmvs_fpn_level_fwd": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_void_p]),
     "casmvs_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p]),
     "casmvs_nhwc_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p]),
 }

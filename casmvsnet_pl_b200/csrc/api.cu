@@ -30,6 +30,8 @@ int conv3d_tc2(const float* x, const float* wpk, const float* scale, const float
                float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
                int w, int kind, int stride, int precision, cudaStream_t st);
 
+namespace tc { void image_cache_clear(); }
+
 struct LayerSpec { int cin, cout, kind, stride; };
 
 // conv0..conv6, conv7, conv9, conv11, prob   (models/mvsnet.py:63-89)
@@ -50,6 +52,12 @@ using namespace casmvs;
 extern "C" int casmvs_version(void) { return CASMVS_VERSION; }
 extern "C" const char* casmvs_last_error(void) { return t_err; }
 extern "C" uint64_t casmvs_launch_count(void) { return g_launches.load(); }
+
+extern "C" int casmvs_invalidate_weight_cache(void) {
+  cudaDeviceSynchronize();
+  casmvs::tc::image_cache_clear();
+  return 0;
+}
 
 extern "C" int casmvs_device_check(int device) {
   int n = 0;

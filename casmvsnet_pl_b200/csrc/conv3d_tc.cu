@@ -311,6 +311,29 @@ float* image_scratch(size_t bytes) {
   return p;
 }
 
+struct CacheEntry { const void* key; int tag; size_t bytes; float* img; };
+static CacheEntry g_cache[256];
+static int g_cache_n = 0;
+
+float* image_cache_lookup(const void* wpk, int tag, size_t bytes, bool* hit) {
+  for (int i = 0; i < g_cache_n; ++i)
+    if (g_cache[i].key == wpk && g_cache[i].tag == tag && g_cache[i].bytes == bytes) {
+      *hit = true;
+      return g_cache[i].img;
+    }
+  *hit = false;
+  if (g_cache_n >= 256) return image_scratch(bytes);       // cache full: fall back to the ring
+  float* img = nullptr;
+  if (cudaMalloc(&img, bytes) != cudaSuccess) return nullptr;
+  g_cache[g_cache_n++] = CacheEntry{wpk, tag, bytes, img};
+  return img;
+}
+
+void image_cache_clear() {
+  for (int i = 0; i < g_cache_n; ++i) cudaFree(g_cache[i].img);
+  g_cache_n = 0;
+}
+
 template <int CIN, int GW>
 static int launch(Params p, cudaStream_t st) {
   using S = Smem<CIN, GW>;
@@ -337,10 +360,13 @@ static int launch(Params p, cudaStream_t st) {
   p.dchunk = dchunk;
   p.nchunks = (p.D + dchunk - 1) / dchunk;
   const int nco = p.cout_total / p.Cout;
-  float* img = image_scratch((size_t)S::kWBytes * nco);
-  if (!img) { set_error("conv3d_tc: cannot allocate the weight-image scratch"); return -2; }
-  build_image_kernel<<<64, 256, 0, st>>>(p.wpk, img, CIN, GW, p.Cout, p.cout_total);
-  if (int rc = after_launch("conv3d_tc/build_image")) return rc;
+  bool hit = false;
+  float* img = image_cache_lookup(p.wpk, 1000 + CIN * 100 + GW, (size_t)S::kWBytes * nco, &hit);
+  if (!img) { set_error("conv3d_tc: cannot allocate the weight image"); return -2; }
+  if (!hit) {
+    build_image_kernel<<<64, 256, 0, st>>>(p.wpk, img, CIN, GW, p.Cout, p.cout_total);
+    if (int rc = after_launch("conv3d_tc/build_image")) return rc;
+  }
   p.bimg = img;
   const long items = (long)p.B * p.nchunks * p.tiles_h * p.tiles_w;
   static int extra = -1;

@@ -381,10 +381,14 @@ static int launch2(Params p, cudaStream_t st) {
   p.nchunks = (Dm + dchunk - 1) / dchunk;
   const long items = cols * p.nchunks;
   const int nco = p.Cout / COUT;
-  float* img = image_scratch((size_t)C::kWBytes * nco);
-  if (!img) { set_error("conv3d_tc2: cannot allocate the weight-image scratch"); return -2; }
-  build_image2_kernel<MODE, CIN, COUT><<<64, 256, 0, st>>>(p.wpk, img, p.Cout);
-  if (int rc = after_launch("conv3d_tc2/build_image")) return rc;
+  bool hit = false;
+  float* img = image_cache_lookup(p.wpk, 2000 + MODE * 10000 + CIN * 100 + COUT,
+                                  (size_t)C::kWBytes * nco, &hit);
+  if (!img) { set_error("conv3d_tc2: cannot allocate the weight image"); return -2; }
+  if (!hit) {
+    build_image2_kernel<MODE, CIN, COUT><<<64, 256, 0, st>>>(p.wpk, img, p.Cout);
+    if (int rc = after_launch("conv3d_tc2/build_image")) return rc;
+  }
   p.bimg = img;
   kfn<<<dim3((unsigned)items, (unsigned)nco), kThreads, C::kTotal, st>>>(p);
   return after_launch("conv3d_tc2");

@@ -1,0 +1,168 @@
+// FeatureNet top-down path, fused (first step): one kernel per pyramid level
+//   feat = up2_bilinear(prev) + conv1x1(c; lat_w) + lat_b        (32 channels, never stored
+//   out  = conv3x3(feat; smooth_w) + smooth_b                     for the finest level)
+// Replaces (reference, relative to /root/reference) FeatureNet._upsample_add + lat{0,1} +
+// smooth{0,1}, models/mvsnet.py:36-52: F.interpolate(x2, bilinear, align_corners=True),
+// three elementwise passes and two cuDNN convolutions over a 32-channel full-resolution
+// tensor (~750 MB of HBM traffic at 640x512x3 views) become ~100 MB.
+// All tensors channels-last fp32; fp32 FMA arithmetic.
+#include "common.cuh"
+
+namespace casmvs {
+
+constexpr int kFpnTile = 16;
+constexpr int kFpnHalo = kFpnTile + 2;
+constexpr int kFpnPix = 36;           // padded pixel pitch (floats) of the smem feature tile
+constexpr int kFpnC = 32;             // pyramid width
+
+template <int COUT>
+__global__ void __launch_bounds__(256)
+fpn_level_kernel(const float* __restrict__ prev,   // (N, h/2, w/2, 32)
+                 const float* __restrict__ c,      // (N, h, w, CLAT)
+                 const float* __restrict__ lat_w,  // (32, CLAT)
+                 const float* __restrict__ lat_b,  // (32)
+                 const float* __restrict__ sm_w,   // (COUT, 32, 3, 3)
+                 const float* __restrict__ sm_b,   // (COUT)
+                 float* __restrict__ feat_out,     // (N, h, w, 32) or null
+                 float* __restrict__ out,          // (N, h, w, COUT)
+                 int h, int w, int CLAT) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_feat = smem;                                   // [18*18][36]
+  float* s_smw = s_feat + kFpnHalo * kFpnHalo * kFpnPix;  // [9][32][COUT]
+  float* s_latw = s_smw + 9 * kFpnC * COUT;               // [CLAT][32]
+  const int n = blockIdx.z;
+  const int y0 = blockIdx.y * kFpnTile, x0 = blockIdx.x * kFpnTile;
+  const int hi = h / 2, wi = w / 2;
+
+  for (int i = threadIdx.x; i < 9 * kFpnC * COUT; i += blockDim.x) {
+    const int co = i % COUT, ci = (i / COUT) % kFpnC, tap = i / (COUT * kFpnC);
+    s_smw[i] = __ldg(sm_w + ((size_t)co * kFpnC + ci) * 9 + tap);
+  }
+  for (int i = threadIdx.x; i < CLAT * kFpnC; i += blockDim.x) {
+    const int ch = i % kFpnC, ci = i / kFpnC;
+    s_latw[i] = __ldg(lat_w + (size_t)ch * CLAT + ci);
+  }
+  __syncthreads();
+
+  // ---- phase 1: the 18x18 halo'd feature tile, 8 channels per work item ----
+  const float sy = hi > 1 ? (float)(hi - 1) / (float)(h - 1) : 0.f;
+  const float sx = wi > 1 ? (float)(wi - 1) / (float)(w - 1) : 0.f;
+  const float* pn = prev + (size_t)n * hi * wi * kFpnC;
+  const float* cn = c + (size_t)n * h * w * CLAT;
+  for (int it = threadIdx.x; it < kFpnHalo * kFpnHalo * 4; it += blockDim.x) {
+    const int g = it & 3, hp = it >> 2;
+    const int ty = hp / kFpnHalo, tx = hp - ty * kFpnHalo;
+    const int y = y0 - 1 + ty, x = x0 - 1 + tx;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    if (y >= 0 && y < h && x >= 0 && x < w) {               // outside the image: zero padding
+      const float fy = sy * (float)y, fx = sx * (float)x;
+      int ya = min((int)fy, hi - 1), xa = min((int)fx, wi - 1);
+      const int yb = min(ya + 1, hi - 1), xb = min(xa + 1, wi - 1);
+      const float ly = fy - (float)ya, lx = fx - (float)xa;
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx),
+                  w11 = ly * lx;
+      const float* p00 = pn + ((size_t)ya * wi + xa) * kFpnC + g * 8;
+      const float* p01 = pn + ((size_t)ya * wi + xb) * kFpnC + g * 8;
+      const float* p10 = pn + ((size_t)yb * wi + xa) * kFpnC + g * 8;
+      const float* p11 = pn + ((size_t)yb * wi + xb) * kFpnC + g * 8;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 a = ldg4(p00 + 4 * q), b = ldg4(p01 + 4 * q), cc = ldg4(p10 + 4 * q),
+                     d = ldg4(p11 + 4 * q);
+        v[4 * q + 0] = a.x * w00 + b.x * w01 + cc.x * w10 + d.x * w11;
+        v[4 * q + 1] = a.y * w00 + b.y * w01 + cc.y * w10 + d.y * w11;
+        v[4 * q + 2] = a.z * w00 + b.z * w01 + cc.z * w10 + d.z * w11;
+        v[4 * q + 3] = a.w * w00 + b.w * w01 + cc.w * w10 + d.w * w11;
+      }
+      const float* cp = cn + ((size_t)y * w + x) * CLAT;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += __ldg(lat_b + g * 8 + k);
+      for (int ci = 0; ci < CLAT; ci += 4) {
+        const float4 cv = ldg4(cp + ci);
+        const float cs[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float* wr = s_latw + (ci + j) * kFpnC + g * 8;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaf(cs[j], wr[k], v[k]);
+        }
+      }
+      if (feat_out && ty >= 1 && ty <= kFpnTile && tx >= 1 && tx <= kFpnTile) {
+        float* fo = feat_out + (((size_t)n * h + y) * w + x) * kFpnC + g * 8;
+        st4(fo, make_float4(v[0], v[1], v[2], v[3]));
+        st4(fo + 4, make_float4(v[4], v[5], v[6], v[7]));
+      }
+    }
+    float* sp = s_feat + hp * kFpnPix + g * 8;
+    *reinterpret_cast<float4*>(sp) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(sp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  __syncthreads();
+
+  // ---- phase 2: 3x3 smoothing conv, one output pixel per thread ----
+  const int ty = threadIdx.x / kFpnTile, tx = threadIdx.x % kFpnTile;
+  const int y = y0 + ty, x = x0 + tx;
+  float acc[COUT];
+#pragma unroll
+  for (int k = 0; k < COUT; ++k) acc[k] = __ldg(sm_b + k);
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const float* fp = s_feat + ((ty + dy) * kFpnHalo + tx + dx) * kFpnPix;
+      const float* wp = s_smw + (dy * 3 + dx) * kFpnC * COUT;
+#pragma unroll
+      for (int ci = 0; ci < kFpnC; ci += 4) {
+        const float4 f = *reinterpret_cast<const float4*>(fp + ci);
+        const float fs[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int k = 0; k < COUT; k += 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(wp + (ci + j) * COUT + k);
+            acc[k] = fmaf(fs[j], wv.x, acc[k]);
+            acc[k + 1] = fmaf(fs[j], wv.y, acc[k + 1]);
+            acc[k + 2] = fmaf(fs[j], wv.z, acc[k + 2]);
+            acc[k + 3] = fmaf(fs[j], wv.w, acc[k + 3]);
+          }
+        }
+      }
+    }
+  }
+  if (y < h && x < w) {
+    float* op = out + (((size_t)n * h + y) * w + x) * COUT;
+#pragma unroll
+    for (int k = 0; k < COUT; k += 4) st4(op + k, make_float4(acc[k], acc[k + 1], acc[k + 2], acc[k + 3]));
+  }
+}
+
+}  // namespace casmvs
+
+using namespace casmvs;
+
+extern "C" int casmvs_fpn_level_fwd(const float* prev, const float* c, const float* lat_w,
+                                    const float* lat_b, const float* smooth_w,
+                                    const float* smooth_b, float* feat_out, float* out, int N,
+                                    int h, int w, int CLAT, int COUT, void* stream) {
+  CASMVS_REQUIRE(prev && c && lat_w && lat_b && smooth_w && smooth_b && out, "fpn_level: null pointer");
+  CASMVS_REQUIRE(N >= 0 && N <= 65535 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0,
+                 "fpn_level: bad dims (h,w even, >= 2)");
+  CASMVS_REQUIRE(CLAT % 4 == 0 && CLAT > 0 && CLAT <= 64, "fpn_level: CLAT must be a multiple of 4");
+  CASMVS_REQUIRE(COUT == 8 || COUT == 16, "fpn_level: COUT must be 8 or 16 (got %d)", COUT);
+  if (N == 0) return 0;
+  dim3 grd((w + kFpnTile - 1) / kFpnTile, (h + kFpnTile - 1) / kFpnTile, N);
+  const size_t smem = (size_t)(kFpnHalo * kFpnHalo * kFpnPix + 9 * kFpnC * COUT + CLAT * kFpnC) * 4;
+  cudaStream_t st = as_stream(stream);
+  if (COUT == 8) {
+    static bool a = false;
+    if (!a) { cudaFuncSetAttribute(fpn_level_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); a = true; }
+    fpn_level_kernel<8><<<grd, 256, smem, st>>>(prev, c, lat_w, lat_b, smooth_w, smooth_b, feat_out, out, h, w, CLAT);
+  } else {
+    static bool a = false;
+    if (!a) { cudaFuncSetAttribute(fpn_level_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); a = true; }
+    fpn_level_kernel<16><<<grd, 256, smem, st>>>(prev, c, lat_w, lat_b, smooth_w, smooth_b, feat_out, out, h, w, CLAT);
+  }
+  return after_launch("fpn_level");
+}

@@ -177,6 +177,11 @@ __device__ __forceinline__ void load_image_async(uint32_t dst_smem, const float*
 // layers on one stream never alias; allocated on first use (run one warm-up forward
 // before capturing a CUDA graph).
 float* image_scratch(size_t bytes);
+// Persistent cache of built images keyed by (packed-weight pointer, kernel tag): inference
+// re-uses the same weights every call, so the prologue kernel runs once per layer.
+// casmvs_invalidate_weight_cache() must be called when packed weights are rewritten in place
+// or their buffer is freed (the Python binding does so whenever it re-packs parameters).
+float* image_cache_lookup(const void* wpk, int tag, size_t bytes, bool* hit);
 
 }  // namespace tc
 }  // namespace casmvs

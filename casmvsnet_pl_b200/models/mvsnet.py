@@ -94,6 +94,15 @@ class FeatureNet(nn.Module):
 
     def _head(self, c0, c1, c2):
         f2 = self.toplayer(c2)
+        if c0.is_cuda and not (self.training or torch.is_grad_enabled()):
+            # fused top-down path: upsample + lateral 1x1 + add + 3x3 smooth in one kernel per
+            # level (csrc/fpn.cu); the 32-channel full-resolution tensor is never stored
+            f1, l1 = ops.fpn_level(f2, c1, self.lat1.weight, self.lat1.bias,
+                                   self.smooth1.weight, self.smooth1.bias, want_feat=True)
+            _, l0 = ops.fpn_level(f1, c0, self.lat0.weight, self.lat0.bias,
+                                  self.smooth0.weight, self.smooth0.bias, want_feat=False)
+            return {"level_0": l0, "level_1": l1,
+                    "level_2": f2.contiguous(memory_format=torch.channels_last)}
         f1 = self._up2(f2) + self.lat1(c1)
         f0 = self._up2(f1) + self.lat0(c0)
         f1 = self.smooth1(f1)

@@ -132,9 +132,16 @@ def homo_warp(src_feat, proj_mat, depth_values):
 
 
 # --------------------------------------------------------------------------- K2
+def invalidate_weight_cache():
+    """Drop the library's cached tensor-core operand images (keyed by packed-weight
+    pointers); called whenever packed weights are re-created."""
+    check(_lib.load().casmvs_invalidate_weight_cache(), "invalidate_weight_cache")
+
+
 def pack_conv3d_weight(weight, kind):
     """torch Conv3d (Cout,Cin,3,3,3) / ConvTranspose3d (Cin,Cout,3,3,3) -> [27][Cin][Cout]."""
     _require_cuda(weight)
+    invalidate_weight_cache()
     if kind == CONV:
         cout, cin = weight.shape[:2]
     else:
@@ -253,3 +260,24 @@ def uniform_hypotheses(init_depth_min, depth_interval, n_depths, B, h, w, device
                                                     _ptr(out), B, n_depths, h, w, _stream()),
           "uniform_hypotheses")
     return out
+
+
+# --------------------------------------------------------------------------- FPN (adjacent)
+def fpn_level(prev, c, lat_w, lat_b, smooth_w, smooth_b, want_feat):
+    """Fused FeatureNet top-down level (models/mvsnet.py:36-52).  prev (N,32,h/2,w/2),
+    c (N,CLAT,h,w) logical NCHW tensors with channels-last storage -> (feat|None, out)."""
+    _require_cuda(prev, c, lat_w, lat_b, smooth_w, smooth_b)
+    pv = prev.contiguous(memory_format=torch.channels_last)
+    cv = c.contiguous(memory_format=torch.channels_last)
+    N, clat, h, w = cv.shape
+    cout = smooth_w.shape[0]
+    assert pv.shape == (N, 32, h // 2, w // 2) and smooth_w.shape[1:] == (32, 3, 3)
+    out = torch.empty((N, cout, h, w), device=c.device, dtype=torch.float32,
+                      memory_format=torch.channels_last)
+    feat = torch.empty((N, 32, h, w), device=c.device, dtype=torch.float32,
+                       memory_format=torch.channels_last) if want_feat else None
+    check(_lib.load().casmvs_fpn_level_fwd(
+        _ptr(pv), _ptr(cv), _ptr(lat_w.detach().contiguous()), _ptr(lat_b.detach().contiguous()),
+        _ptr(smooth_w.detach().contiguous()), _ptr(smooth_b.detach().contiguous()), _ptr(feat),
+        _ptr(out), N, h, w, clat, cout, _stream()), "fpn_level")
+    return feat, out

@@ -106,6 +106,10 @@ size_t casmvs_packed_conv3d_weight_floats(int Cin, int Cout);
 /* w_torch: Conv3d layout (Cout,Cin,3,3,3) or ConvTranspose3d layout (Cin,Cout,3,3,3) */
 int casmvs_pack_conv3d_weights(const float* w_torch, int kind, int Cin, int Cout,
                                float* w_packed, void* stream);
+/* The tensor-core kernels keep a per-process cache of operand images keyed by the
+ * w_packed pointer.  Call this after rewriting packed weights in place or freeing them
+ * (synchronises the device). */
+int casmvs_invalidate_weight_cache(void);
 int casmvs_conv3d_fwd(const float* x, const float* w_packed, const float* scale,
                       const float* shift, float slope, const float* skip, float* y,
                       int B, int Cin, int Cout, int D, int h, int w, /* INPUT dims */
@@ -155,6 +159,17 @@ int casmvs_depth_hypotheses_fwd(const float* cur, int upsample, float half_range
 int casmvs_uniform_hypotheses_fwd(float depth_min, float step, const float* depth_min_dev,
                                   const float* step_dev, float* out,
                                   int B, int D, int h, int w, void* stream);
+
+/* ---- FeatureNet top-down path, fused (adjacent to the hot path) ----
+ * One pyramid level of models/mvsnet.py:36-52:
+ *   feat = upsample_x2_bilinear(prev, align_corners=True) + conv1x1(c, lat_w) + lat_b   (32 ch)
+ *   out  = conv3x3(feat, smooth_w, pad 1) + smooth_b
+ * prev (N,h/2,w/2,32), c (N,h,w,CLAT), out (N,h,w,COUT), feat_out (N,h,w,32) or NULL; all
+ * channels-last.  lat_w (32,CLAT[,1,1]) and smooth_w (COUT,32,3,3) in torch layout. */
+int casmvs_fpn_level_fwd(const float* prev, const float* c, const float* lat_w,
+                         const float* lat_b, const float* smooth_w, const float* smooth_b,
+                         float* feat_out, float* out, int N, int h, int w, int CLAT, int COUT,
+                         void* stream);
 
 /* ---- layout helpers ------------------------------------------------------ */
 /* (N,C,S) -> (N,S,C) and back, S = product of spatial dims. */

@@ -275,3 +275,27 @@ def test_layout_helpers_roundtrip():
     z = torch.empty_like(x)
     _lib.check(lib.casmvs_nhwc_to_nchw(ops._ptr(y), ops._ptr(z), 3, 16, 77, s))
     assert torch.equal(z, x)
+
+
+# ----------------------------------------------------------------------------- FPN (adjacent)
+@pytest.mark.parametrize("clat,cout,hw", [(16, 16, (20, 28)), (8, 8, (34, 50))])
+def test_fused_fpn_level_vs_torch_cpu(clat, cout, hw):
+    """csrc/fpn.cu against the reference formula (models/mvsnet.py:36-52) in fp32 on the CPU."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(clat)
+    h, w = hw
+    N = 2
+    prev = torch.randn(N, 32, h // 2, w // 2, generator=g)
+    c = torch.randn(N, clat, h, w, generator=g)
+    lat_w = torch.randn(32, clat, 1, 1, generator=g) * 0.2
+    lat_b = torch.randn(32, generator=g) * 0.1
+    sm_w = torch.randn(cout, 32, 3, 3, generator=g) * 0.1
+    sm_b = torch.randn(cout, generator=g) * 0.1
+    feat = F.interpolate(prev, scale_factor=2, mode="bilinear", align_corners=True) + F.conv2d(c, lat_w, lat_b)
+    want = F.conv2d(feat, sm_w, sm_b, padding=1)
+    gf, got = ops.fpn_level(prev.to(DEV), c.to(DEV), lat_w.to(DEV), lat_b.to(DEV), sm_w.to(DEV),
+                            sm_b.to(DEV), want_feat=True)
+    e1 = stats(f"fpn feat clat={clat}", gf.cpu(), feat)
+    e2 = stats(f"fpn out  cout={cout}", got.cpu(), want)
+    assert e1.max() < 2e-5 and e2.max() < 5e-5     # fp32 FMA, different summation order only
+    assert ops.is_channels_last_feats(got)
