@@ -299,3 +299,35 @@ def test_fused_fpn_level_vs_torch_cpu(clat, cout, hw):
     e2 = stats(f"fpn out  cout={cout}", got.cpu(), want)
     assert e1.max() < 2e-5 and e2.max() < 5e-5     # fp32 FMA, different summation order only
     assert ops.is_channels_last_feats(got)
+
+
+# ----------------------------------------------------------------------------- K2 on tcgen05
+@pytest.mark.parametrize("kind,cin,cout,dims", [
+    ("conv1", 8, 8, (5, 20, 13)), ("conv1", 16, 8, (16, 40, 24)), ("conv1", 32, 8, (8, 32, 40)),
+    ("conv1", 16, 16, (6, 32, 24)), ("conv1", 32, 32, (4, 16, 16)), ("conv1", 8, 1, (8, 32, 16)),
+    ("conv1", 64, 64, (3, 16, 24)),
+    ("conv2", 8, 16, (8, 32, 40)), ("conv2", 16, 32, (6, 20, 24)), ("conv2", 32, 64, (4, 16, 16)),
+    ("convT", 16, 8, (5, 18, 11)), ("convT", 32, 16, (3, 16, 16)), ("convT", 64, 32, (2, 16, 24))])
+def test_tensor_core_conv_vs_cuda_core_fp32(kind, cin, cout, dims):
+    """Every CostRegNet layer type on the tcgen05 path (tf32 operands, fp32 accumulate) against
+    the fp32 CUDA-core kernel on the same inputs (ragged tiles, halos, skip, ABN epilogue).
+    Operands carry 10 mantissa bits => relative error ~2^-11 per product, K = 27*Cin terms."""
+    g = torch.Generator().manual_seed(cin * 131 + cout)
+    x = torch.randn(2, cin, *dims, generator=g).to(DEV)
+    scale = (torch.rand(cout, generator=g) + 0.5).to(DEV)
+    shift = (torch.randn(cout, generator=g) * 0.1).to(DEV)
+    if kind == "convT":
+        wt = (torch.randn(cin, cout, 3, 3, 3, generator=g) * 0.1).to(DEV)
+        k, stride = ops.CONV_TRANSPOSE, 2
+        skip = torch.randn(2, cout, *[2 * d for d in dims], generator=g).to(DEV)
+    else:
+        wt = (torch.randn(cout, cin, 3, 3, 3, generator=g) * 0.1).to(DEV)
+        k, stride = ops.CONV, (1 if kind == "conv1" else 2)
+        skip = torch.randn(2, cout, *dims, generator=g).to(DEV) if kind == "conv1" and cout > 1 else None
+    wp = ops.pack_conv3d_weight(wt, k)
+    ref = ops.conv3d(x, wp, cin, cout, scale, shift, 0.01, skip, k, stride, ops.FP32)
+    got = ops.conv3d(x, wp, cin, cout, scale, shift, 0.01, skip, k, stride, ops.TF32)
+    assert got.shape == ref.shape
+    err = stats(f"tc {kind} {cin}->{cout}", got.cpu(), ref.cpu())
+    assert err.max() < 1.5e-3 * ref.abs().max().item()
+    assert not torch.isnan(got).any()
