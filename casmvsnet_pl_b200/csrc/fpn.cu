@@ -138,9 +138,35 @@ fpn_level_kernel(const float* __restrict__ prev,   // (N, h/2, w/2, 32)
   }
 }
 
+// x[..., c] = lrelu(x[..., c] + bias[c]) in place on a channels-last tensor (C % 4 == 0):
+// the tail of a folded conv+ABN block when the conv itself comes from cuDNN.
+__global__ void __launch_bounds__(256)
+bias_lrelu_kernel(float* __restrict__ x, const float* __restrict__ bias, float slope, size_t n4,
+                  int C) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)((i * 4) % (size_t)C);
+  float4 v = *reinterpret_cast<float4*>(x + i * 4);
+  const float4 b = ldg4(bias + c);
+  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+  v.x = v.x >= 0.f ? v.x : v.x * slope; v.y = v.y >= 0.f ? v.y : v.y * slope;
+  v.z = v.z >= 0.f ? v.z : v.z * slope; v.w = v.w >= 0.f ? v.w : v.w * slope;
+  *reinterpret_cast<float4*>(x + i * 4) = v;
+}
+
 }  // namespace casmvs
 
 using namespace casmvs;
+
+extern "C" int casmvs_bias_lrelu_nhwc(float* x, const float* bias, float slope, size_t numel,
+                                      int C, void* stream) {
+  CASMVS_REQUIRE(x && bias, "bias_lrelu: null pointer");
+  CASMVS_REQUIRE(C > 0 && C % 4 == 0 && numel % (size_t)C == 0, "bias_lrelu: C %% 4 != 0 or ragged");
+  if (numel == 0) return 0;
+  const size_t n4 = numel / 4;
+  bias_lrelu_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, as_stream(stream)>>>(x, bias, slope, n4, C);
+  return after_launch("bias_lrelu");
+}
 
 extern "C" int casmvs_fpn_level_fwd(const float* prev, const float* c, const float* lat_w,
                                     const float* lat_b, const float* smooth_w,

@@ -42,3 +42,68 @@ class GraphedCascade:
             self.proj.copy_(proj_mats, non_blocking=True)
         self.graph.replay()
         return self.out
+
+
+class PipelinedCascade:
+    """Host-buffer streaming inference: the eval loop's H2D copy of view i+1 and the D2H read of
+    view i-1 overlap the graph replay of view i (two slots, each with its own static inputs,
+    captured graph and pinned result buffers; one copy stream, one compute stream).
+
+        pipe = PipelinedCascade(model, imgs_example, proj_example, depth_min, depth_interval)
+        for imgs_h, proj_h in views:            # pinned host tensors
+            done = pipe.submit(imgs_h, proj_h)  # returns the results of the view submitted
+            ...                                 # `depth` slots earlier (or None while filling)
+        tail = pipe.drain()
+    Results are (depth_0, confidence_2) pinned host tensors, what eval.py:224-226 reads back.
+    """
+
+    def __init__(self, model, imgs, proj_mats, init_depth_min, depth_interval, slots=2):
+        self.slots = [GraphedCascade(model, imgs, proj_mats, init_depth_min, depth_interval,
+                                     warmup=3 if i == 0 else 1) for i in range(slots)]
+        self.copy_stream = torch.cuda.Stream()      # H2D
+        self.d2h_stream = torch.cuda.Stream()       # D2H (separate: it waits on compute)
+        self.compute = torch.cuda.current_stream()
+        self.h2d_done = [torch.cuda.Event() for _ in range(slots)]
+        self.compute_done = [torch.cuda.Event() for _ in range(slots)]
+        self.d2h_done = [torch.cuda.Event() for _ in range(slots)]
+        self.out_h = []
+        for g in self.slots:
+            self.out_h.append((torch.empty(g.out["depth_0"].shape).pin_memory(),
+                               torch.empty(g.out["confidence_2"].shape).pin_memory()))
+        self.n = 0
+        self.pending = []
+
+    def submit(self, imgs_h, proj_h):
+        i = self.n % len(self.slots)
+        g = self.slots[i]
+        ret = None
+        if len(self.pending) == len(self.slots):          # slot i still holds an older view
+            ret = self._collect()
+        with torch.cuda.stream(self.copy_stream):
+            # the slot's previous replay must have consumed its inputs before they are overwritten
+            self.copy_stream.wait_event(self.compute_done[i])
+            g.imgs.copy_(imgs_h, non_blocking=True)
+            g.proj.copy_(proj_h, non_blocking=True)
+            self.h2d_done[i].record(self.copy_stream)
+        self.compute.wait_event(self.h2d_done[i])
+        g.graph.replay()
+        self.compute_done[i].record(self.compute)
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(self.compute_done[i])
+            self.out_h[i][0].copy_(g.out["depth_0"], non_blocking=True)
+            self.out_h[i][1].copy_(g.out["confidence_2"], non_blocking=True)
+            self.d2h_done[i].record(self.d2h_stream)
+        self.pending.append(i)
+        self.n += 1
+        return ret
+
+    def _collect(self):
+        i = self.pending.pop(0)
+        self.d2h_done[i].synchronize()
+        return self.out_h[i]
+
+    def drain(self):
+        out = []
+        while self.pending:
+            out.append(self._collect())
+        return out

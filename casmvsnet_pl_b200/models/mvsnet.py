@@ -77,7 +77,14 @@ class FeatureNet(nn.Module):
 
         def run(t, lo, hi):
             for w, b, stride, pad, slope in cache[lo:hi]:
-                t = F.leaky_relu_(F.conv2d(t, w, b, stride, pad), slope)
+                if t.is_cuda:
+                    # cuDNN conv, then ONE fused bias + LeakyReLU pass (csrc/fpn.cu)
+                    t = F.conv2d(t, w, None, stride, pad)
+                    if not t.is_contiguous(memory_format=torch.channels_last):
+                        t = t.contiguous(memory_format=torch.channels_last)
+                    t = ops.bias_lrelu_(t, b, slope)
+                else:
+                    t = F.leaky_relu_(F.conv2d(t, w, b, stride, pad), slope)
             return t
         c0 = run(x, 0, 2)
         c1 = run(c0, 2, 5)

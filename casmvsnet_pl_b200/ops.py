@@ -281,3 +281,12 @@ def fpn_level(prev, c, lat_w, lat_b, smooth_w, smooth_b, want_feat):
         _ptr(smooth_w.detach().contiguous()), _ptr(smooth_b.detach().contiguous()), _ptr(feat),
         _ptr(out), N, h, w, clat, cout, _stream()), "fpn_level")
     return feat, out
+
+
+def bias_lrelu_(x, bias, slope):
+    """In-place LeakyReLU(x + bias[c]) on a channels-last (N,C,h,w) tensor."""
+    _require_cuda(x, bias)
+    assert x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 4 == 0
+    check(_lib.load().casmvs_bias_lrelu_nhwc(_ptr(x), _ptr(bias), float(slope), x.numel(),
+                                             x.shape[1], _stream()), "bias_lrelu")
+    return x

@@ -171,6 +171,11 @@ int casmvs_fpn_level_fwd(const float* prev, const float* c, const float* lat_w,
                          float* feat_out, float* out, int N, int h, int w, int CLAT, int COUT,
                          void* stream);
 
+/* In-place x[...,c] = LeakyReLU(x[...,c] + bias[c]) on a channels-last tensor (C % 4 == 0):
+ * the epilogue of a folded conv + eval-mode ABN block (models/modules.py:8-18). */
+int casmvs_bias_lrelu_nhwc(float* x, const float* bias, float slope, size_t numel, int C,
+                           void* stream);
+
 /* ---- layout helpers ------------------------------------------------------ */
 /* (N,C,S) -> (N,S,C) and back, S = product of spatial dims. */
 int casmvs_nchw_to_nhwc(const float* in, float* out, int N, int C, size_t S, void* stream);
