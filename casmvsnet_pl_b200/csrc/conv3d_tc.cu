@@ -106,14 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) 
 
   // ---- one-time setup ----
   if (threadIdx.x == 0) TC_STAMP(3, 0, 0);
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < SLOTS; ++i) {
-      mbar_init(bar_full + 8 * i, kProducerThreads);
-      mbar_init(bar_empty + 8 * i, 1);
-    }
-    for (int i = 0; i < 32; ++i) mbar_init(bar_tfull + 8 * i, 1);
-    fence_barrier_init();
-  }
+  init_barriers(bar_full, bar_empty, bar_tfull, SLOTS);
   if (warp == 0) tmem_alloc(smem_u32((const void*)s_tmem_ptr), tmem_cols);
   // B operand image (built once per launch by build_image_kernel) -> smem
   const int co_base = blockIdx.y * p.Cout;
@@ -141,7 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) 
   tc_fence_after();
   if (threadIdx.x == 0) TC_STAMP(3, 0, 1);
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < kMmaWarp) {
     // ===================== producers: input bricks -> smem ring =====================
     const int ptid = threadIdx.x - 128;
     for (int it = 0; it < nslices; ++it) {
@@ -174,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc_kernel(const Params p) 
     cp_async_wait<0>();
     fence_proxy_async();
     mbar_arrive(bar_full + 8 * ((nslices - 1) % SLOTS));
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (single thread) =====================
     // The issuing thread is a scalar loop: anything computed per MMA costs ~5 cycles per
     // dependent instruction, and the tensor pipe retires a small MMA in ~45 cycles

@@ -101,14 +101,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p)
   const int s_first = MODE == MODE_S2 ? 2 * g0 - 1 : g0;
   const uint32_t tmem_cols = tmem_cols_for2(p.dchunk * GW);
 
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < SLOTS; ++i) {
-      mbar_init(bar_full + 8 * i, kProducerThreads);
-      mbar_init(bar_empty + 8 * i, 1);
-    }
-    for (int i = 0; i < 32; ++i) mbar_init(bar_tfull + 8 * i, 1);
-    fence_barrier_init();
-  }
+  init_barriers(bar_full, bar_empty, bar_tfull, SLOTS);
   if (warp == 0) tmem_alloc(smem_u32((const void*)s_tmem_ptr), tmem_cols);
 
   // B operand image (built once per launch by build_image2_kernel) -> smem
@@ -132,7 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p)
   __syncthreads();
   tc_fence_after();
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < kMmaWarp) {
     // ===================== producers =====================
     const int ptid = threadIdx.x - 128;
     for (int it = 0; it < nslices; ++it) {
@@ -168,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv3d_tc2_kernel(const Params p)
     cp_async_wait<0>();
     fence_proxy_async();
     mbar_arrive(bar_full + 8 * ((nslices - 1) % SLOTS));
-  } else if (warp == 8) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (warp-uniform, elect-predicated) =====================
     constexpr uint32_t a_lbo = BW * 16;
     constexpr uint32_t a_sbo = (MODE == MODE_S2 ? 2 : 1) * CQ * BW * 16;

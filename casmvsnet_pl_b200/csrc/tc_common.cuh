@@ -9,8 +9,11 @@ namespace tc {
 constexpr int kTileW = 8, kTileH = 16;           // M = 128
 constexpr int kHaloW = kTileW + 2, kHaloH = kTileH + 2;
 constexpr int kSlots = 4;
-constexpr int kThreads = 9 * 32;
-constexpr int kProducerThreads = 128;
+// warps 0-3 epilogue (TMEM lane quadrants), kProducerWarps producer warps, last warp MMA issuer
+constexpr int kProducerWarps = 4;   // 8 was slower: 416 threads x 64-80 regs leave one CTA per SM
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kMmaWarp = 4 + kProducerWarps;
+constexpr int kThreads = (kMmaWarp + 1) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -169,6 +172,15 @@ __device__ __forceinline__ void load_image_async(uint32_t dst_smem, const float*
     cp_async16(dst_smem + i, reinterpret_cast<const char*>(src) + i, 16u);
   cp_async_commit();
   cp_async_wait<0>();
+}
+// barrier init spread over the first threads of the CTA (one mbarrier each)
+__device__ __forceinline__ void init_barriers(uint32_t bar_full, uint32_t bar_empty,
+                                              uint32_t bar_tfull, int slots) {
+  const int t = threadIdx.x;
+  if (t < slots) mbar_init(bar_full + 8 * t, kProducerThreads);
+  else if (t < 2 * slots) mbar_init(bar_empty + 8 * (t - slots), 1);
+  else if (t < 2 * slots + 32) mbar_init(bar_tfull + 8 * (t - 2 * slots), 1);
+  if (t < 2 * slots + 32) fence_barrier_init();
 }
 
 // Library-owned scratch for the per-launch B operand images (built by a tiny prologue
