@@ -290,6 +290,12 @@ __global__ void build_image_kernel(const float* __restrict__ wpk, float* __restr
   }
 }
 
+int build_stride1_image(const float* wpk, float* img, int CIN, int GW, int chunk, int cout_total,
+                        cudaStream_t st) {
+  build_image_kernel<<<64, 256, 0, st>>>(wpk, img, CIN, GW, chunk, cout_total);
+  return after_launch("conv3d_tc/build_image");
+}
+
 float* image_scratch(size_t bytes) {
   constexpr int kRing = 8;
   constexpr size_t kSlot = 512 * 1024;
@@ -357,8 +363,7 @@ static int launch(Params p, cudaStream_t st) {
   float* img = image_cache_lookup(p.wpk, 1000 + CIN * 100 + GW, (size_t)S::kWBytes * nco, &hit);
   if (!img) { set_error("conv3d_tc: cannot allocate the weight image"); return -2; }
   if (!hit) {
-    build_image_kernel<<<64, 256, 0, st>>>(p.wpk, img, CIN, GW, p.Cout, p.cout_total);
-    if (int rc = after_launch("conv3d_tc/build_image")) return rc;
+    if (int rc = build_stride1_image(p.wpk, img, CIN, GW, p.Cout, p.cout_total, st)) return rc;
   }
   p.bimg = img;
   const long items = (long)p.B * p.nchunks * p.tiles_h * p.tiles_w;

@@ -194,6 +194,10 @@ float* image_scratch(size_t bytes);
 // casmvs_invalidate_weight_cache() must be called when packed weights are rewritten in place
 // or their buffer is freed (the Python binding does so whenever it re-packs parameters).
 float* image_cache_lookup(const void* wpk, int tag, size_t bytes, bool* hit);
+// B operand image of the stride-1 kernels: [chunk][kh][kw][CIN/4][3*GW][4], tf32-rounded,
+// column group g holds the weights of kd = 2 - g (shared by conv3d_tc.cu and conv3d_tma.cu)
+int build_stride1_image(const float* wpk, float* img, int CIN, int GW, int chunk, int cout_total,
+                        cudaStream_t st);
 
 }  // namespace tc
 }  // namespace casmvs

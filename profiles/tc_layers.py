@@ -10,7 +10,8 @@ shapes = []
 for l, (D, H, W) in {2: (48, 128, 160), 1: (32, 256, 320), 0: (8, 512, 640)}.items():
     C = 8 * 2 ** l
     shapes += [(f"l{l}.conv0", C, 8, (D, H, W)), (f"l{l}.conv2", 16, 16, (D // 2, H // 2, W // 2)),
-               (f"l{l}.conv4", 32, 32, (D // 4, H // 4, W // 4)), (f"l{l}.prob", 8, 1, (D, H, W))]
+               (f"l{l}.conv4", 32, 32, (D // 4, H // 4, W // 4)),
+               (f"l{l}.conv6", 64, 64, (D // 8, H // 8, W // 8)), (f"l{l}.prob", 8, 1, (D, H, W))]
 for i, (name, cin, cout, dims) in enumerate(shapes):
     if only >= 0 and i != only:
         continue

@@ -23,7 +23,7 @@ print(f"kernel {e0.elapsed_time(e1)*1e3:.1f} us for cin={cin} cout={cout} dims={
 t = dbg.cpu().reshape(4, 64, 4)
 t0 = int(t[3, 0, 0])
 print("setup cycles", int(t[3, 0, 1]) - t0)
-for it in range(16):
+for it in range(44):
     pr = [int(v) - t0 if v else -1 for v in t[0, it]]
     mm = [int(v) - t0 if v else -1 for v in t[1, it]]
     ep = [int(v) - t0 if v else -1 for v in t[2, it]]
