@@ -29,6 +29,10 @@ int conv3d_tc(const float* x, const float* wpk, const float* scale, const float*
 int conv3d_tma(const float* x, const float* wpk, const float* scale, const float* shift,
                float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
                int w, int kind, int stride, int precision, cudaStream_t st);
+// conv3d_tma_n8.cu (tcgen05 + TMA, stride-1 layers with Cout <= 8: kd and kw folded into N)
+int conv3d_tma_n8(const float* x, const float* wpk, const float* scale, const float* shift,
+                  float slope, const float* skip, float* y, int B, int Cin, int Cout, int D,
+                  int h, int w, int kind, int stride, int precision, cudaStream_t st);
 // conv3d_tc3.cu (tcgen05, stride-1 layers with Cout <= 8: kd and kh folded into N)
 int conv3d_tc3(const float* x, const float* wpk, const float* scale, const float* shift,
                float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
@@ -103,6 +107,9 @@ extern "C" int casmvs_conv3d_fwd(const float* x, const float* w_packed, const fl
     int rc = conv3d_tc3(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
                         stride, precision, st);
     if (rc <= 0) return rc;  // handled (0) or failed (<0); 1 = shape not covered
+    rc = conv3d_tma_n8(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
+                       stride, precision, st);
+    if (rc <= 0) return rc;
     rc = conv3d_tma(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
                     stride, precision, st);
     if (rc <= 0) return rc;

@@ -24,12 +24,12 @@
 // thread), 5 MMA issuer.  Ring full barriers are armed with expect_tx and completed by the
 // TMA unit; ring empty barriers by tcgen05.commit; per output slice tfull (MMA -> epilogue)
 // and tempty (epilogue -> MMA, accumulator read and re-zeroed) barriers.
-#include <cuda.h>
 #include <cudaTypedefs.h>
 #include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma_common.cuh"
 
 namespace casmvs {
 
@@ -80,20 +80,6 @@ struct Smem {
 
 __host__ __device__ constexpr int tmem_cols_for(int n) {
   return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512;
-}
-
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
-      "r"(c3), "r"(c4)
-      : "memory");
 }
 
 template <int CIN, int GW, int SLOTS_>
@@ -325,14 +311,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 
 // Tensor maps are pure functions of (pointer, shape, box): memoised, since inference calls
 // every layer with the same workspace pointers each step.
-struct MapEntry { const void* x; int B, D, H, W, C, CB; CUtensorMap map; };
+struct MapEntry { const void* x; int B, D, H, W, C, CB, bw, bh; CUtensorMap map; };
 static MapEntry g_maps[128];
 static int g_maps_n = 0, g_maps_next = 0;
 
-static const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, int C, int CB) {
+const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, int C, int CB, int box_w,
+                             int box_h) {
   for (int i = 0; i < g_maps_n; ++i) {
     const MapEntry& e = g_maps[i];
-    if (e.x == x && e.B == B && e.D == D && e.H == H && e.W == W && e.C == C && e.CB == CB)
+    if (e.x == x && e.B == B && e.D == D && e.H == H && e.W == W && e.C == C && e.CB == CB &&
+        e.bw == box_w && e.bh == box_h)
       return &e.map;
   }
   auto enc = encode_fn();
@@ -344,7 +332,7 @@ static const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, 
                               (cuuint64_t)B};
   const cuuint64_t gstr[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4,
                               (cuuint64_t)D * H * W * C * 4};
-  const cuuint32_t box[5] = {(cuuint32_t)CB, (cuuint32_t)kHaloW, (cuuint32_t)kHaloH, 1, 1};
+  const cuuint32_t box[5] = {(cuuint32_t)CB, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
   const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   const CUtensorMapSwizzle sw = CB * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : CB * 4 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
@@ -358,11 +346,10 @@ static const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, 
               (int)r, C, W, H, D, B);
     return nullptr;
   }
-  e.x = x; e.B = B; e.D = D; e.H = H; e.W = W; e.C = C; e.CB = CB;
+  e.x = x; e.B = B; e.D = D; e.H = H; e.W = W; e.C = C; e.CB = CB; e.bw = box_w; e.bh = box_h;
   return &e.map;
 }
 
-static int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
 
 template <int CIN, int GW, int SLOTS>
 static int launch(const float* x, const float* wpk, Params p, cudaStream_t st) {
@@ -379,7 +366,7 @@ static int launch(const float* x, const float* wpk, Params p, cudaStream_t st) {
     }
     attr_set = true;
   }
-  const CUtensorMap* map = input_map(x, p.B, p.D, p.H, p.W, CIN, S::CB);
+  const CUtensorMap* map = input_map(x, p.B, p.D, p.H, p.W, CIN, S::CB, kHaloW, kHaloH);
   if (!map) return -2;
   // resident CTAs per SM by shared memory (1 KB per CTA is reserved by the system); the TMEM
   // of all of them must fit in 512 columns: one accumulator group (GW columns) per output slice

@@ -1,0 +1,437 @@
+// K2 (tensor-core variant, TMA producer, narrow outputs) — stride-1 3x3x3 convolution with
+// Cout <= 8: conv0 of every stage and the `prob` head, the layers that carry most of
+// CostRegNet's bytes.  sm_100a only.
+//
+// Replaces (reference, relative to /root/reference): ConvBnReLU3D conv0
+// (models/mvsnet.py:63, models/modules.py:21-31) and the prob head (models/mvsnet.py:89,103).
+//
+// profiles/microbench/umma_rate.cu: a tf32 M=128 MMA costs 44.6 cycles for any N <= ~89, and
+// with the TMA producer conv3d_tma.cu is bound by exactly that (9*Cin/8 MMAs of N = 48 per
+// input slice keep the tensor pipe 100 % busy).  Here BOTH the kd and the kw taps are folded
+// into N, which cuts the MMA count per input slice to 3*Cin/8 (N = 80):
+//   * GEMM rows: M = 128 = 4 image rows x 32 brick columns.  The TMA brick of a slice is
+//     [6 rows][32 columns][CB channels] (voxel-major, swizzled by the row size), so the sixteen
+//     8-voxel row groups of the A operand are evenly spaced (SBO = 8 voxels) and the kh tap is a
+//     start-address shift of one brick row;
+//   * GEMM columns: 9 groups of 8 = (kd, kw) x Cout: D[m][(kd,kw,co)] = sum_{kh,ci}
+//     x[s][h+kh-1][i][ci] * W[kd][kh][kw][ci][co] for brick column i;
+//   * the kw taps are recombined in the epilogue: output column c of the tile needs
+//     D[c][kw=0] + D[c+1][kw=1] + D[c+2][kw=2], i.e. a shift of 1 and 2 TMEM lanes INSIDE one
+//     warp (a warp owns one image row of 32 brick columns): two __shfl_down per value, no
+//     shared memory and no cross-warp barrier.  30 of the 32 brick columns produce outputs.
+// Everything else is as in conv3d_tma.cu: persistent CTAs, 6 warps (0-3 epilogue, 4 TMA
+// producer, 5 MMA issuer), linear TMEM accumulators (24 columns per output slice) that every
+// MMA accumulates into and the epilogue re-zeroes after reading, full/empty ring barriers and
+// tfull/tempty accumulator barriers.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tma_common.cuh"
+
+namespace casmvs {
+namespace tma8 {
+
+using namespace casmvs::tc;
+using casmvs::tma::mbar_expect_tx;
+using casmvs::tma::tma_load_5d;
+
+constexpr int kThreads8 = 6 * 32;
+constexpr int kProdWarp = 4, kIssueWarp = 5;
+constexpr int kRowsOut = 4;     // image rows per tile (= epilogue warps)
+constexpr int kBH = 6;          // brick rows (with halo)
+constexpr int kBW = 32;         // brick columns (with halo) = lanes of a warp
+constexpr int kColsOut = 30;    // output columns per tile
+constexpr int kG = 24;          // accumulator columns per output slice: 3 kw x 8 channels
+constexpr int kBRows = 80;      // B rows per kh: 3 kd x 24 + 8 zero rows (N must be % 16)
+
+struct Params {
+  const float* bimg;   // [kh][CIN/4][80][4], tf32-rounded
+  const float* scale;  // [Cout] or null
+  const float* shift;  // [Cout] or null
+  const float* skip;   // (B,D,H,W,Cout) or null
+  float* y;            // (B,D,H,W,Cout)
+  float slope;
+  int B, D, H, W, Cout;
+  int tiles_w, tiles_h, nchunks, dchunk;
+  int round_out;
+  long long* dbg;
+};
+#define N8_STAMP(role, idx, k)                                                                  \
+  do {                                                                                          \
+    if (p.dbg && blockIdx.x == 0 && (idx) < 64) p.dbg[((role) * 64 + (idx)) * 4 + (k)] = clock64(); \
+  } while (0)
+
+template <int CIN, int SLOTS_>
+struct Smem {
+  static constexpr int SLOTS = SLOTS_;
+  static constexpr int ROWB = CIN * 4;                              // bytes per voxel = swizzle span
+  static constexpr int kSlotBytes = kBH * kBW * ROWB;               // 6 KB x CIN/8: 1024-aligned
+  static constexpr int kWBytes = 3 * CIN * kBRows * 4;              // [kh][cq][80][4]
+  static constexpr int kRingOff = 0;
+  static constexpr int kWOff = SLOTS * kSlotBytes;
+  static constexpr int kParamOff = kWOff + kWBytes;                 // scale/shift [2][8]
+  static constexpr int kBarOff = kParamOff + 2 * 8 * 4;
+  // barriers: full[8] @0, empty[8] @64, tmem ptr @128, tfull[32] @192, tempty[32] @448
+  static constexpr int kTotal = kBarOff + 192 + 32 * 8 + 32 * 8 + 1024;   // + alignment slack
+  static constexpr uint32_t kLayout = ROWB == 128 ? 2u : ROWB == 64 ? 4u : 6u;
+};
+
+__host__ __device__ constexpr int tmem_cols_for8(int n) {
+  return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512;
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),
+                 "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// the loaded registers are only valid after the wait: tie them to it so that the compiler
+// cannot schedule a use above it
+__device__ __forceinline__ void tmem_ld_wait(float (&v)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]),
+                 "+f"(v[6]), "+f"(v[7])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_zero8(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};"
+               ::"r"(taddr), "r"(z)
+               : "memory");
+}
+
+template <int CIN, int SLOTS_>
+__global__ void __launch_bounds__(kThreads8, 1)
+conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
+  using S = Smem<CIN, SLOTS_>;
+  constexpr int SLOTS = S::SLOTS;
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t s_raw = smem_u32(smem_raw);
+  const uint32_t s_base = (s_raw + 1023u) & ~1023u;
+  unsigned char* smem = smem_raw + (s_base - s_raw);
+  const uint32_t s_ring = s_base + S::kRingOff, s_w = s_base + S::kWOff,
+                 s_bar = s_base + S::kBarOff;
+  float* s_param = reinterpret_cast<float*>(smem + S::kParamOff);
+  const uint32_t bar_full = s_bar, bar_empty = s_bar + 64, bar_tfull = s_bar + 192,
+                 bar_tempty = s_bar + 448;
+  volatile uint32_t* s_tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + S::kBarOff + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // dchunk groups + 8 spill columns (N is rounded up to a multiple of 16: the extra 8 columns of
+  // a 24- or 72-column MMA land on the next group's first 8 columns)
+  const uint32_t tmem_cols = tmem_cols_for8(p.dchunk * kG + 8);
+  const int total_items = p.B * p.nchunks * p.tiles_h * p.tiles_w;
+
+  // ---- one-time setup ----
+  if (threadIdx.x == 0) N8_STAMP(3, 0, 0);
+  {
+    const int t = threadIdx.x;
+    if (t < SLOTS) mbar_init(bar_full + 8 * t, 1);
+    else if (t < 2 * SLOTS) mbar_init(bar_empty + 8 * (t - SLOTS), 1);
+    else if (t >= 32 && t < 64) mbar_init(bar_tfull + 8 * (t - 32), 1);
+    else if (t >= 64 && t < 96) mbar_init(bar_tempty + 8 * (t - 64), 128);
+    if (t < 96) fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(smem_u32((const void*)s_tmem_ptr), tmem_cols);
+  load_image_async(s_w, p.bimg, S::kWBytes);
+  for (int i = threadIdx.x; i < 8; i += kThreads8) {
+    s_param[i] = (i < p.Cout) ? (p.scale ? __ldg(p.scale + i) : 1.f) : 0.f;
+    s_param[8 + i] = (i < p.Cout) ? (p.shift ? __ldg(p.shift + i) : 0.f) : 0.f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem_ptr;
+  if (warp < 4) {
+    for (int c = 0; c < p.dchunk * kG + 8; c += 8)
+      tmem_zero8(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (threadIdx.x == 0) N8_STAMP(3, 0, 1);
+  uint32_t gs = 0;                                  // slices processed before this item (all roles)
+  int ep = 0;                                       // items processed by this CTA
+  for (int item0 = blockIdx.x; item0 < total_items; item0 += gridDim.x, ++ep) {
+    int item = item0;
+    const int tw = item % p.tiles_w; item /= p.tiles_w;
+    const int th = item % p.tiles_h; item /= p.tiles_h;
+    const int ck = item % p.nchunks;
+    const int b = item / p.nchunks;
+    const int w0 = tw * kColsOut, h0 = th * kRowsOut;
+    const int d0 = ck * p.dchunk, d1 = min(p.D, d0 + p.dchunk);
+    const int nd = d1 - d0;
+    const int nslices = nd + 2;                     // input slices d0-1 .. d1
+
+    if (warp == kProdWarp) {
+      // ===================== producer: one TMA load per slice =====================
+      if (lane == 0) {
+        for (int it = 0; it < nslices; ++it) {
+          const uint32_t g = gs + it;
+          const int slot = g % SLOTS;
+          N8_STAMP(0, g, 0);
+          if (g >= (uint32_t)SLOTS) mbar_wait(bar_empty + 8 * slot, ((g / SLOTS) - 1) & 1);
+          N8_STAMP(0, g, 1);
+          mbar_expect_tx(bar_full + 8 * slot, S::kSlotBytes);
+          tma_load_5d(s_ring + slot * S::kSlotBytes, &xmap, bar_full + 8 * slot, 0, w0 - 1,
+                      h0 - 1, d0 - 1 + it, b);
+          N8_STAMP(0, g, 2);
+        }
+      }
+      __syncwarp();
+    } else if (warp == kIssueWarp) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t a_lbo = 16, a_sbo = 8 * S::ROWB;               // 8-voxel group stride
+      constexpr uint32_t b_lbo = kBRows * 16, b_sbo = 128;
+      const uint32_t elected = elect_one();
+      const uint64_t a_desc0 = make_desc(s_ring, a_lbo, a_sbo) | ((uint64_t)S::kLayout << 61);
+      const uint64_t b_desc0 = make_desc(s_w, b_lbo, b_sbo);
+      const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+      int waited = 0;                               // groups whose tempty has been consumed
+      for (int it = 0; it < nslices; ++it) {
+        const uint32_t g = gs + it;
+        // input slice `it` feeds output slices j = it - kd, kd = 0,1,2, clipped to [0,nd):
+        // columns [j_lo*24, (j_hi+1)*24) (+8 pad columns when the count is odd),
+        // B rows [(2-kd_hi)*24, ...)
+        const int kd_lo = max(0, it - (nd - 1)), kd_hi = min(2, it);
+        const int cnt = kd_hi - kd_lo + 1;
+        const int j_lo = it - kd_hi;
+        const uint32_t idesc = make_idesc(128, cnt == 1 ? 32 : cnt == 2 ? 48 : 80);
+        const uint32_t acc = tmem_base + j_lo * kG;
+        if (lane == 0) N8_STAMP(1, g, 0);
+        mbar_wait(bar_full + 8 * (g % SLOTS), (g / SLOTS) & 1);
+        if (lane == 0) N8_STAMP(1, g, 1);
+        // Every group this slice touches -- including the pad columns on group it+1 -- must
+        // have been drained and re-zeroed by the epilogue of the previous item.
+        if (ep > 0) {
+          const int need = min(it + 1, p.dchunk - 1);
+          for (; waited <= need; ++waited) mbar_wait(bar_tempty + 8 * waited, (ep - 1) & 1);
+        }
+        if (lane == 0) N8_STAMP(1, g, 2);
+        tc_fence_after();
+        const uint32_t a_lo0 = (uint32_t)a_desc0 + (((g % SLOTS) * S::kSlotBytes) >> 4);
+        const uint32_t b_lo0 = (uint32_t)b_desc0 + (((2 - kd_hi) * kG * 16) >> 4);
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+          for (int k8 = 0; k8 < CIN / 8; ++k8) {
+            const uint32_t a_off = (kh * kBW * S::ROWB + k8 * 32) >> 4;
+            const uint32_t b_off = (kh * (CIN * kBRows * 4) + k8 * 2 * kBRows * 16) >> 4;
+            umma_tf32(acc, a_lo0 + a_off, a_hi, b_lo0 + b_off, b_hi, idesc, elected);
+          }
+        }
+        if (it >= 2) umma_commit(bar_tfull + 8 * (it - 2), elected);   // slice it-2 complete
+        umma_commit(bar_empty + 8 * (g % SLOTS), elected);             // smem slot free
+        if (lane == 0) N8_STAMP(1, g, 3);
+      }
+      // groups this (short) chunk did not use go through the same handshake (empty -> full) so
+      // that every barrier sees exactly one completion per item; the commit (not a plain
+      // arrive) orders the epilogue's clean-up of the pad columns after the last MMA
+      for (int j = nd; j < p.dchunk; ++j) {
+        if (ep > 0) {
+          for (; waited <= j; ++waited) mbar_wait(bar_tempty + 8 * waited, (ep - 1) & 1);
+        }
+        umma_commit(bar_tfull + 8 * j, elected);
+      }
+    } else {
+      // ===================== epilogue warps 0..3: one image row each =====================
+      const int oh = h0 + warp, ow = w0 + lane;
+      const bool writes = lane < kColsOut && oh < p.H && ow < p.W;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+      for (int j = 0; j < p.dchunk; ++j) {
+        if (threadIdx.x == 0) N8_STAMP(2, ep * p.dchunk + j, 0);
+        mbar_wait(bar_tfull + 8 * j, ep & 1);
+        if (threadIdx.x == 0) N8_STAMP(2, ep * p.dchunk + j, 1);
+        tc_fence_after();
+        if (j >= nd) {
+          // unused group: only its first 8 columns can have been written (pad columns of the
+          // last slice's MMA, non-zero weights) -- clean them for the next item
+          if (j == nd) {
+            tmem_zero8(lane_base + j * kG);
+            tmem_wait_st();
+            tc_fence_before();
+          }
+          mbar_arrive(bar_tempty + 8 * j);
+          continue;
+        }
+        float a0[8], a1[8], a2[8];
+        tmem_ld8(lane_base + j * kG, a0);
+        tmem_ld8(lane_base + j * kG + 8, a1);
+        tmem_ld8(lane_base + j * kG + 16, a2);
+        tmem_ld_wait(a0);
+        tmem_ld_wait(a1);
+        tmem_ld_wait(a2);
+        tmem_zero8(lane_base + j * kG);
+        tmem_zero8(lane_base + j * kG + 8);
+        tmem_zero8(lane_base + j * kG + 16);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8 * j);           // group j drained and zero again
+        if (threadIdx.x == 0) N8_STAMP(2, ep * p.dchunk + j, 2);
+        // out[c] = D_kw0[c] + D_kw1[c+1] + D_kw2[c+2]   (c = brick column = lane)
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float s1 = __shfl_down_sync(0xffffffffu, a1[k], 1);
+          const float s2 = __shfl_down_sync(0xffffffffu, a2[k], 2);
+          const float t = fmaf(a0[k] + s1 + s2, s_param[k], s_param[8 + k]);
+          v[k] = t >= 0.f ? t : t * p.slope;
+        }
+        if (writes) {
+          const size_t o = ((((size_t)b * p.D + (d0 + j)) * p.H + oh) * p.W + ow) * p.Cout;
+          if (p.Cout == 8) {
+            if (p.skip) {
+              const float4 s0 = ldg4(p.skip + o), s1 = ldg4(p.skip + o + 4);
+              v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
+              v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+            }
+            if (p.round_out) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] = to_tf32(v[k]);
+            }
+            st4(p.y + o, make_float4(v[0], v[1], v[2], v[3]));
+            st4(p.y + o + 4, make_float4(v[4], v[5], v[6], v[7]));
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              if (k < p.Cout) {
+                float tt = v[k];
+                if (p.skip) tt += __ldg(p.skip + o + k);
+                p.y[o + k] = p.round_out ? to_tf32(tt) : tt;
+              }
+            }
+          }
+        }
+      }
+    }
+    gs += nslices;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// [kh][cq][row = g*24 + kw*8 + co][4], g = 2 - kd; rows 72..79 zero; tf32-rounded
+__global__ void build_image_n8_kernel(const float* __restrict__ wpk, float* __restrict__ img,
+                                      int CIN, int Cout) {
+  const int CQ = CIN / 4;
+  const int total = 3 * CIN * kBRows;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int jq = i & 3;
+    const int row = (i >> 2) % kBRows;
+    const int r = (i >> 2) / kBRows;       // kh*CQ + cq
+    const int cq = r % CQ, kh = r / CQ;
+    const int ci = cq * 4 + jq;
+    float v = 0.f;
+    if (row < 72) {
+      const int g = row / kG, kw = (row % kG) / 8, co = row % 8;
+      const int kd = 2 - g;
+      if (co < Cout)
+        v = to_tf32(__ldg(wpk + ((size_t)((kd * 3 + kh) * 3 + kw) * CIN + ci) * Cout + co));
+    }
+    img[i] = v;
+  }
+}
+
+template <int CIN, int SLOTS>
+static int launch8(const float* x, const float* wpk, Params p, cudaStream_t st) {
+  using S = Smem<CIN, SLOTS>;
+  auto kfn = conv3d_tma_n8_kernel<CIN, SLOTS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S::kTotal);
+    if (e != cudaSuccess) {
+      set_error("conv3d_tma_n8: cannot opt in to %d B of shared memory: %s", S::kTotal,
+                cudaGetErrorString(e));
+      return -2;
+    }
+    attr_set = true;
+  }
+  const CUtensorMap* map = tma::input_map(x, p.B, p.D, p.H, p.W, CIN, CIN, kBW, kBH);
+  if (!map) return -2;
+  static int per_sm_env = -1, dchunk_env = -1;
+  if (per_sm_env < 0) {
+    const char* e = getenv("CASMVS_N8_PER_SM");
+    per_sm_env = e ? atoi(e) : 0;
+    const char* d = getenv("CASMVS_N8_DCHUNK");
+    dchunk_env = d ? atoi(d) : 0;
+  }
+  // resident CTAs per SM: as many as shared memory allows (1 KB per CTA is reserved by the
+  // system), at most 4.  Measured on cfg2 (profiles/r1_n8_per_sm.txt): more, shorter-chunk CTAs
+  // beat fewer, longer ones for Cin = 8 and 16 (the epilogue's store latency is what has to be
+  // hidden); Cin = 32 fits two.
+  const int smem_limit = (228 * 1024) / (S::kTotal + 1024);
+  int per_sm = smem_limit < 4 ? smem_limit : 4;
+  if (per_sm_env > 0 && per_sm_env < per_sm) per_sm = per_sm_env;
+  if (per_sm < 1) per_sm = 1;
+  int cap = (tma::pow2_floor(512 / per_sm) - 8) / kG;
+  if (cap > 21) cap = 21;
+  if (dchunk_env > 0 && dchunk_env < cap) cap = dchunk_env;
+  // equal chunks: nchunks = ceil(D / cap), dchunk = ceil(D / nchunks)
+  int nchunks = (p.D + cap - 1) / cap;
+  int dchunk = (p.D + nchunks - 1) / nchunks;
+  p.tiles_w = (p.W + kColsOut - 1) / kColsOut;
+  p.tiles_h = (p.H + kRowsOut - 1) / kRowsOut;
+  // small volumes: more, shorter chunks until every resident CTA has an item
+  const long cols = (long)p.B * p.tiles_w * p.tiles_h;
+  while (dchunk > 4 && cols * ((p.D + dchunk - 1) / dchunk) < (long)num_sms() * per_sm)
+    dchunk = (dchunk + 1) / 2;
+  p.dchunk = dchunk;
+  p.nchunks = (p.D + dchunk - 1) / dchunk;
+  bool hit = false;
+  float* img = image_cache_lookup(wpk, 8000 + CIN, (size_t)S::kWBytes, &hit);
+  if (!img) { set_error("conv3d_tma_n8: cannot allocate the weight image"); return -2; }
+  if (!hit) {
+    build_image_n8_kernel<<<32, 256, 0, st>>>(wpk, img, CIN, p.Cout);
+    if (int rc = after_launch("conv3d_tma_n8/build_image")) return rc;
+  }
+  p.bimg = img;
+  const long items = (long)p.B * p.nchunks * p.tiles_h * p.tiles_w;
+  const long resident = (long)num_sms() * per_sm;
+  const long gx = items < resident ? items : resident;
+  kfn<<<dim3((unsigned)gx), kThreads8, S::kTotal, st>>>(*map, p);
+  return after_launch("conv3d_tma_n8");
+}
+
+}  // namespace tma8
+
+// Returns 0 when handled, 1 when the layer shape is left to the other kernels.
+int conv3d_tma_n8(const float* x, const float* wpk, const float* scale, const float* shift,
+                  float slope, const float* skip, float* y, int B, int Cin, int Cout, int D,
+                  int h, int w, int kind, int stride, int precision, cudaStream_t st) {
+  static int enabled = -1, round_out = 1;
+  static long long* dbg = nullptr;
+  if (enabled < 0) {
+    const char* e = getenv("CASMVS_N8");
+    enabled = e ? atoi(e) : 1;
+    if (const char* s = getenv("CASMVS_TC_ROUND")) round_out = atoi(s);
+    if (const char* s = getenv("CASMVS_TC_DBG")) dbg = (long long*)strtoull(s, nullptr, 0);
+  }
+  if (!enabled || precision != CASMVS_TF32) return 1;
+  if (kind != CASMVS_CONV || stride != 1) return 1;
+  if (!(Cin == 8 || Cin == 16 || Cin == 32) || Cout > 8) return 1;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
+  tma8::Params p;
+  p.scale = scale; p.shift = shift; p.skip = skip; p.y = y;
+  p.slope = slope; p.B = B; p.D = D; p.H = h; p.W = w; p.Cout = Cout;
+  p.dbg = dbg;
+  p.round_out = (round_out && Cout > 1) ? 1 : 0;   // the prob head feeds the softmax: keep fp32
+  if (Cin == 8) return tma8::launch8<8, 4>(x, wpk, p, st);
+  if (Cin == 16) return tma8::launch8<16, 4>(x, wpk, p, st);
+  return tma8::launch8<32, 3>(x, wpk, p, st);
+}
+
+}  // namespace casmvs

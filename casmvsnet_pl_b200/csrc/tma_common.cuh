@@ -1,0 +1,34 @@
+// TMA helpers shared by the TMA-fed tcgen05 convolution kernels (sm_100a only).
+#pragma once
+#include <cuda.h>
+
+#include "tc_common.cuh"
+
+namespace casmvs {
+namespace tma {
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4)
+      : "memory");
+}
+
+// Tiled tensor map over the activation tensor x (B,D,H,W,C) viewed as {C, W, H, D, B} with box
+// {CB, box_w, box_h, 1, 1}, swizzle = CB*4 bytes (128/64/32), out-of-bounds elements zero-filled
+// (= the convolution's zero padding).  Memoised by (pointer, shape, box); null + casmvs error
+// when the driver entry point is missing or the encode fails.  (conv3d_tma.cu)
+const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, int C, int CB, int box_w,
+                             int box_h);
+
+inline int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
+
+}  // namespace tma
+}  // namespace casmvs
