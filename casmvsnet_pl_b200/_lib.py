@@ -12,8 +12,9 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcasmvs.so")
 
 NCHW, NHWC = 0, 1
 ROUND_TF32 = 256
+KEEP_FP32_OUT = 256      # OR-ed into conv3d precision
 FP32, TF32, TF32X3 = 0, 1, 2
-CONV, CONV_TRANSPOSE = 0, 1
+CONV, CONV_TRANSPOSE, CONV_PLANAR = 0, 1, 2
 PRECISIONS = {"fp32": FP32, "tf32": TF32, "tf32x3": TF32X3}
 
 # name -> (restype, argtypes); must list every symbol include/casmvs.h declares
@@ -48,6 +49,9 @@ SIGNATURES = {
     "casmvs_uniform_hypotheses_fwd": (c_int, [c_float, c_float, c_void_p, c_void_p, c_void_p,
                                               c_int, c_int, c_int, c_int, c_void_p]),
     "casmvs_fpn_level_fwd": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_void_p]),
+    "casmvs_fpn_merge_fwd": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
+    "casmvs_conv2d_rgb8_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p] + [c_int] * 4 + [c_void_p]),
+    "casmvs_bias_act_nhwc": (c_int, [c_void_p, c_void_p, c_float, c_size_t, c_int, c_int, c_void_p]),
     "casmvs_bias_lrelu_nhwc": (c_int, [c_void_p, c_void_p, c_float, c_size_t, c_int, c_void_p]),
     "casmvs_nchw_to_nhwc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p]),
     "casmvs_nhwc_to_nchw": (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p]),

@@ -97,34 +97,47 @@ extern "C" int casmvs_conv3d_fwd(const float* x, const float* w_packed, const fl
   CASMVS_REQUIRE(x && w_packed && y, "conv3d: null pointer");
   CASMVS_REQUIRE(B >= 0 && Cin > 0 && Cout > 0 && D > 0 && h > 0 && w > 0, "conv3d: bad dims");
   CASMVS_REQUIRE(Cin % 4 == 0, "conv3d: Cin must be a multiple of 4 (got %d)", Cin);
-  CASMVS_REQUIRE(kind == CASMVS_CONV || kind == CASMVS_CONV_TRANSPOSE, "conv3d: bad kind");
-  CASMVS_REQUIRE(kind == CASMVS_CONV ? (stride == 1 || stride == 2) : stride == 2,
+  CASMVS_REQUIRE(kind == CASMVS_CONV || kind == CASMVS_CONV_TRANSPOSE ||
+                     kind == CASMVS_CONV_PLANAR, "conv3d: bad kind");
+  CASMVS_REQUIRE(kind == CASMVS_CONV ? (stride == 1 || stride == 2)
+                 : kind == CASMVS_CONV_PLANAR ? stride == 1 : stride == 2,
                  "conv3d: unsupported stride %d", stride);
-  CASMVS_REQUIRE(precision >= CASMVS_FP32 && precision <= CASMVS_TF32X3, "conv3d: bad precision");
+  const int flags = precision & ~0xff;
+  precision &= 0xff;
+  CASMVS_REQUIRE(precision >= CASMVS_FP32 && precision <= CASMVS_TF32X3 &&
+                     (flags & ~CASMVS_KEEP_FP32_OUT) == 0, "conv3d: bad precision");
   if (B == 0) return 0;
   cudaStream_t st = as_stream(stream);
   if (precision != CASMVS_FP32) {
-    int rc = conv3d_tc3(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
-                        stride, precision, st);
+    const int pf = precision | flags;
+    int rc = 1;
+    if (kind != CASMVS_CONV_PLANAR)
+      rc = conv3d_tc3(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
+                      stride, precision, st);
     if (rc <= 0) return rc;  // handled (0) or failed (<0); 1 = shape not covered
     rc = conv3d_tma_n8(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
-                       stride, precision, st);
+                       stride, pf, st);
     if (rc <= 0) return rc;
     rc = conv3d_tma(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
-                    stride, precision, st);
+                    stride, pf, st);
     if (rc <= 0) return rc;
-    rc = conv3d_tc(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
-                   stride, precision, st);
-    if (rc <= 0) return rc;
-    rc = conv3d_tc2(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
-                    stride, precision, st);
-    if (rc <= 0) return rc;  // 1 = shape not covered -> CUDA cores
+    if (kind != CASMVS_CONV_PLANAR) {
+      rc = conv3d_tc(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
+                     stride, precision, st);
+      if (rc <= 0) return rc;
+      rc = conv3d_tc2(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
+                      stride, precision, st);
+      if (rc <= 0) return rc;  // 1 = shape not covered -> CUDA cores
+    }
   }
   // in the tf32 modes every stored activation is tf32-rounded (unbiased operand for
   // the tensor-core layers); the prob head (Cout == 1) feeds the softmax and stays fp32
-  const int round_out = (precision == CASMVS_TF32 && Cout > 1) ? 1 : 0;
-  return conv3d_direct(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
-                       stride, st, round_out);
+  const int round_out =
+      (precision == CASMVS_TF32 && Cout > 1 && !(flags & CASMVS_KEEP_FP32_OUT)) ? 1 : 0;
+  // a planar (1x3x3) kernel is a 3x3x3 kernel whose outer planes are zero: the CUDA-core
+  // kernel runs it as such
+  return conv3d_direct(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w,
+                       kind == CASMVS_CONV_PLANAR ? CASMVS_CONV : kind, stride, st, round_out);
 }
 
 // ---- CostRegNet driver ------------------------------------------------------

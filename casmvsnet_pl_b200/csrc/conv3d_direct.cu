@@ -195,6 +195,10 @@ __global__ void pack_w_kernel(const float* __restrict__ wt, float* __restrict__ 
   const int co = i % Cout;
   const int ci = (i / Cout) % Cin;
   const int tap = i / (Cout * Cin);
+  if (kind == CASMVS_CONV_PLANAR) {        // (Cout,Cin,3,3) -> centre plane, outer planes zero
+    wp[i] = (tap >= 9 && tap < 18) ? wt[((size_t)co * Cin + ci) * 9 + (tap - 9)] : 0.f;
+    return;
+  }
   const size_t src = kind == CASMVS_CONV ? ((size_t)co * Cin + ci) * 27 + tap
                                          : ((size_t)ci * Cout + co) * 27 + tap;
   wp[i] = wt[src];
@@ -256,7 +260,8 @@ extern "C" size_t casmvs_packed_conv3d_weight_floats(int Cin, int Cout) {
 extern "C" int casmvs_pack_conv3d_weights(const float* w_torch, int kind, int Cin, int Cout,
                                           float* w_packed, void* stream) {
   CASMVS_REQUIRE(w_torch && w_packed, "pack_conv3d_weights: null pointer");
-  CASMVS_REQUIRE(kind == CASMVS_CONV || kind == CASMVS_CONV_TRANSPOSE, "pack: bad kind");
+  CASMVS_REQUIRE(kind == CASMVS_CONV || kind == CASMVS_CONV_TRANSPOSE ||
+                     kind == CASMVS_CONV_PLANAR, "pack: bad kind");
   CASMVS_REQUIRE(Cin > 0 && Cout > 0, "pack: bad dims");
   const int n = 27 * Cin * Cout;
   pack_w_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(w_torch, w_packed, kind, Cin, Cout);

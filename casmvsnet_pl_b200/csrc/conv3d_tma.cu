@@ -51,6 +51,7 @@ struct Params {
   int cout_total;         // channel count of the output tensor; blockIdx.y selects the chunk
   int tiles_w, tiles_h, nchunks, dchunk;
   int round_out;        // round the stored activations to tf32 (unbiased next-layer operand)
+  int planar;           // 1x3x3 kernel: input slice s feeds output slice s only (kd = 1)
   long long* dbg;       // optional timeline of CTA 0: [role][slice][4] clock64 stamps
 };
 #define TMA_STAMP(role, idx, k)                                                                 \
@@ -150,7 +151,8 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
     const int w0 = tw * kTileW, h0 = th * kTileH;
     const int d0 = ck * p.dchunk, d1 = min(p.D, d0 + p.dchunk);
     const int nd = d1 - d0;
-    const int nslices = nd + 2;                     // input slices d0-1 .. d1
+    const int halo = p.planar ? 0 : 1;
+    const int nslices = nd + 2 * halo;              // input slices d0-halo .. d1-1+halo
 
     if (warp == kProdWarp) {
       // ===================== producer: one TMA load per brick =====================
@@ -166,7 +168,7 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
 #pragma unroll
           for (int nb = 0; nb < S::NB; ++nb)
             tma_load_5d(dst + nb * S::kBrickBytes, &xmap, bar_full + 8 * slot, nb * S::CB,
-                        w0 - 1, h0 - 1, d0 - 1 + it, b);
+                        w0 - 1, h0 - 1, d0 - halo + it, b);
           TMA_STAMP(0, g, 2);
         }
       }
@@ -186,15 +188,16 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
         const uint32_t g = gs + it;
         // input slice `it` feeds output slices j = it - kd, kd = 0,1,2, clipped to [0,nd):
         // columns [j_lo*GW, (j_hi+1)*GW), B rows [(2-kd_hi)*GW, (3-kd_lo)*GW)
-        const int kd_lo = max(0, it - (nd - 1)), kd_hi = min(2, it);
-        const int j_lo = it - kd_hi;
+        const int kd_lo = p.planar ? 1 : max(0, it - (nd - 1));
+        const int kd_hi = p.planar ? 1 : min(2, it);
+        const int j_lo = p.planar ? it : it - kd_hi;
         const uint32_t idesc = make_idesc(128, (kd_hi - kd_lo + 1) * GW);
         const uint32_t acc = tmem_base + j_lo * GW;
         if (lane == 0) TMA_STAMP(1, g, 0);
         mbar_wait(bar_full + 8 * (g % SLOTS), (g / SLOTS) & 1);
         if (lane == 0) TMA_STAMP(1, g, 1);
         // first touch of group `it` in this item: the epilogue must have drained + re-zeroed it
-        if (ep > 0 && it < nd) mbar_wait(bar_tempty + 8 * it, (ep - 1) & 1);
+        if (ep > 0 && it < nd) mbar_wait(bar_tempty + 8 * it, (ep - 1) & 1);   // (it < nd always when planar)
         if (lane == 0) TMA_STAMP(1, g, 2);
         tc_fence_after();
         const uint32_t a_lo0 = (uint32_t)a_desc0 + (((g % SLOTS) * S::kSlotBytes) >> 4);
@@ -210,7 +213,8 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
             umma_tf32(acc, a_lo0 + a_off, a_hi, b_lo0 + b_off, b_hi, idesc, elected);
           }
         }
-        if (it >= 2) umma_commit(bar_tfull + 8 * (it - 2), elected);   // slice it-2 complete
+        if (p.planar) umma_commit(bar_tfull + 8 * it, elected);        // slice it complete
+        else if (it >= 2) umma_commit(bar_tfull + 8 * (it - 2), elected);   // slice it-2 complete
         umma_commit(bar_empty + 8 * (g % SLOTS), elected);             // smem slot free
         if (lane == 0) TMA_STAMP(1, g, 3);
       }
@@ -411,7 +415,8 @@ static int launch(const float* x, const float* wpk, Params p, cudaStream_t st) {
 // Returns 0 when handled, 1 when the layer shape is left to the other kernels.
 int conv3d_tma(const float* x, const float* wpk, const float* scale, const float* shift,
                float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
-               int w, int kind, int stride, int precision, cudaStream_t st) {
+               int w, int kind, int stride, int precision_flags, cudaStream_t st) {
+  const int precision = precision_flags & 0xff;
   static int enabled = -1, round_out = 1;
   static long long* dbg = nullptr;
   if (enabled < 0) {
@@ -421,7 +426,7 @@ int conv3d_tma(const float* x, const float* wpk, const float* scale, const float
     if (const char* s = getenv("CASMVS_TC_DBG")) dbg = (long long*)strtoull(s, nullptr, 0);
   }
   if (!enabled || precision != CASMVS_TF32) return 1;
-  if (kind != CASMVS_CONV || stride != 1) return 1;
+  if ((kind != CASMVS_CONV && kind != CASMVS_CONV_PLANAR) || stride != 1) return 1;
   const bool deep = Cin == 64 && Cout == 64;          // conv6: 16-channel Cout slices
   if (!deep && (!(Cin == 8 || Cin == 16 || Cin == 32) || Cout > 32)) return 1;
   // the TMA global strides must be multiples of 16 B and the base 16 B aligned
@@ -434,7 +439,9 @@ int conv3d_tma(const float* x, const float* wpk, const float* scale, const float
   p.tiles_h = (h + tc::kTileH - 1) / tc::kTileH;
   const int npad = p.Cout <= 16 ? 16 : 32;
   p.dbg = dbg;
-  p.round_out = (round_out && Cout > 1) ? 1 : 0;   // the prob head feeds the softmax: keep fp32
+  p.planar = kind == CASMVS_CONV_PLANAR ? 1 : 0;
+  // the prob head feeds the softmax: keep fp32; callers can ask for unrounded outputs
+  p.round_out = (round_out && Cout > 1 && !(precision_flags & CASMVS_KEEP_FP32_OUT)) ? 1 : 0;
 #define TMA_CASE(CI, NP, SL) \
   if (Cin == CI && npad == NP) return tma::launch<CI, NP, SL>(x, wpk, p, st);
   TMA_CASE(8, 16, 4) TMA_CASE(8, 32, 4) TMA_CASE(16, 16, 4) TMA_CASE(16, 32, 4)

@@ -55,6 +55,7 @@ struct Params {
   int B, D, H, W, Cout;
   int tiles_w, tiles_h, nchunks, dchunk;
   int round_out;
+  int planar;          // 1x3x3 kernel: input slice s feeds output slice s only (kd = 1)
   long long* dbg;
 };
 #define N8_STAMP(role, idx, k)                                                                  \
@@ -169,7 +170,8 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
     const int w0 = tw * kColsOut, h0 = th * kRowsOut;
     const int d0 = ck * p.dchunk, d1 = min(p.D, d0 + p.dchunk);
     const int nd = d1 - d0;
-    const int nslices = nd + 2;                     // input slices d0-1 .. d1
+    const int halo = p.planar ? 0 : 1;
+    const int nslices = nd + 2 * halo;              // input slices d0-halo .. d1-1+halo
 
     if (warp == kProdWarp) {
       // ===================== producer: one TMA load per slice =====================
@@ -182,7 +184,7 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
           N8_STAMP(0, g, 1);
           mbar_expect_tx(bar_full + 8 * slot, S::kSlotBytes);
           tma_load_5d(s_ring + slot * S::kSlotBytes, &xmap, bar_full + 8 * slot, 0, w0 - 1,
-                      h0 - 1, d0 - 1 + it, b);
+                      h0 - 1, d0 - halo + it, b);
           N8_STAMP(0, g, 2);
         }
       }
@@ -201,9 +203,10 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
         // input slice `it` feeds output slices j = it - kd, kd = 0,1,2, clipped to [0,nd):
         // columns [j_lo*24, (j_hi+1)*24) (+8 pad columns when the count is odd),
         // B rows [(2-kd_hi)*24, ...)
-        const int kd_lo = max(0, it - (nd - 1)), kd_hi = min(2, it);
+        const int kd_lo = p.planar ? 1 : max(0, it - (nd - 1));
+        const int kd_hi = p.planar ? 1 : min(2, it);
         const int cnt = kd_hi - kd_lo + 1;
-        const int j_lo = it - kd_hi;
+        const int j_lo = p.planar ? it : it - kd_hi;
         const uint32_t idesc = make_idesc(128, cnt == 1 ? 32 : cnt == 2 ? 48 : 80);
         const uint32_t acc = tmem_base + j_lo * kG;
         if (lane == 0) N8_STAMP(1, g, 0);
@@ -228,7 +231,8 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
             umma_tf32(acc, a_lo0 + a_off, a_hi, b_lo0 + b_off, b_hi, idesc, elected);
           }
         }
-        if (it >= 2) umma_commit(bar_tfull + 8 * (it - 2), elected);   // slice it-2 complete
+        if (p.planar) umma_commit(bar_tfull + 8 * it, elected);        // slice it complete
+        else if (it >= 2) umma_commit(bar_tfull + 8 * (it - 2), elected);   // slice it-2 complete
         umma_commit(bar_empty + 8 * (g % SLOTS), elected);             // smem slot free
         if (lane == 0) N8_STAMP(1, g, 3);
       }
@@ -325,7 +329,7 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
 
 // [kh][cq][row = g*24 + kw*8 + co][4], g = 2 - kd; rows 72..79 zero; tf32-rounded
 __global__ void build_image_n8_kernel(const float* __restrict__ wpk, float* __restrict__ img,
-                                      int CIN, int Cout) {
+                                      int CIN, int Cout, int planar) {
   const int CQ = CIN / 4;
   const int total = 3 * CIN * kBRows;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -338,7 +342,9 @@ __global__ void build_image_n8_kernel(const float* __restrict__ wpk, float* __re
     if (row < 72) {
       const int g = row / kG, kw = (row % kG) / 8, co = row % 8;
       const int kd = 2 - g;
-      if (co < Cout)
+      // planar: only the centre plane (the pad columns of its N = 32 MMA fall on the next
+      // output slice's accumulator, so the rows after group 1 MUST be zero)
+      if (co < Cout && (!planar || kd == 1))
         v = to_tf32(__ldg(wpk + ((size_t)((kd * 3 + kh) * 3 + kw) * CIN + ci) * Cout + co));
     }
     img[i] = v;
@@ -392,10 +398,10 @@ static int launch8(const float* x, const float* wpk, Params p, cudaStream_t st) 
   p.dchunk = dchunk;
   p.nchunks = (p.D + dchunk - 1) / dchunk;
   bool hit = false;
-  float* img = image_cache_lookup(wpk, 8000 + CIN, (size_t)S::kWBytes, &hit);
+  float* img = image_cache_lookup(wpk, 8000 + CIN + (p.planar ? 500 : 0), (size_t)S::kWBytes, &hit);
   if (!img) { set_error("conv3d_tma_n8: cannot allocate the weight image"); return -2; }
   if (!hit) {
-    build_image_n8_kernel<<<32, 256, 0, st>>>(wpk, img, CIN, p.Cout);
+    build_image_n8_kernel<<<32, 256, 0, st>>>(wpk, img, CIN, p.Cout, p.planar);
     if (int rc = after_launch("conv3d_tma_n8/build_image")) return rc;
   }
   p.bimg = img;
@@ -411,7 +417,8 @@ static int launch8(const float* x, const float* wpk, Params p, cudaStream_t st) 
 // Returns 0 when handled, 1 when the layer shape is left to the other kernels.
 int conv3d_tma_n8(const float* x, const float* wpk, const float* scale, const float* shift,
                   float slope, const float* skip, float* y, int B, int Cin, int Cout, int D,
-                  int h, int w, int kind, int stride, int precision, cudaStream_t st) {
+                  int h, int w, int kind, int stride, int precision_flags, cudaStream_t st) {
+  const int precision = precision_flags & 0xff;
   static int enabled = -1, round_out = 1;
   static long long* dbg = nullptr;
   if (enabled < 0) {
@@ -421,14 +428,16 @@ int conv3d_tma_n8(const float* x, const float* wpk, const float* scale, const fl
     if (const char* s = getenv("CASMVS_TC_DBG")) dbg = (long long*)strtoull(s, nullptr, 0);
   }
   if (!enabled || precision != CASMVS_TF32) return 1;
-  if (kind != CASMVS_CONV || stride != 1) return 1;
+  if ((kind != CASMVS_CONV && kind != CASMVS_CONV_PLANAR) || stride != 1) return 1;
   if (!(Cin == 8 || Cin == 16 || Cin == 32) || Cout > 8) return 1;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return 1;
   tma8::Params p;
   p.scale = scale; p.shift = shift; p.skip = skip; p.y = y;
   p.slope = slope; p.B = B; p.D = D; p.H = h; p.W = w; p.Cout = Cout;
   p.dbg = dbg;
-  p.round_out = (round_out && Cout > 1) ? 1 : 0;   // the prob head feeds the softmax: keep fp32
+  p.planar = kind == CASMVS_CONV_PLANAR ? 1 : 0;
+  // the prob head feeds the softmax: keep fp32; callers can ask for unrounded outputs
+  p.round_out = (round_out && Cout > 1 && !(precision_flags & CASMVS_KEEP_FP32_OUT)) ? 1 : 0;
   if (Cin == 8) return tma8::launch8<8, 4>(x, wpk, p, st);
   if (Cin == 16) return tma8::launch8<16, 4>(x, wpk, p, st);
   return tma8::launch8<32, 3>(x, wpk, p, st);

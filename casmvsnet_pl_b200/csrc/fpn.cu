@@ -138,11 +138,143 @@ fpn_level_kernel(const float* __restrict__ prev,   // (N, h/2, w/2, 32)
   }
 }
 
+__device__ __forceinline__ float round_tf32_if(float x, int on) {
+  if (!on) return x;
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// feat[n,y,x,:] = up2_bilinear(prev)[n,y,x,:] + lat_w @ c[n,y,x,:] + lat_b  (32 channels).
+// Four threads per pixel, 8 channels each: 4 x 32 B of `prev` per bilinear corner, the pixel's
+// CLAT lateral inputs (shared by the four threads through L1), one 32 B store.  HBM-bound:
+// reads c + prev (a quarter of the pixels), writes 128 B per pixel.
+__global__ void __launch_bounds__(256)
+fpn_merge_kernel(const float* __restrict__ prev,   // (N, h/2, w/2, 32) or null
+                 const float* __restrict__ c,      // (N, h, w, CLAT)
+                 const float* __restrict__ lat_w,  // (32, CLAT)
+                 const float* __restrict__ lat_b,  // (32)
+                 float* __restrict__ feat,         // (N, h, w, 32)
+                 int N, int h, int w, int CLAT, int round_out) {
+  extern __shared__ __align__(16) float s_latw[];   // [CLAT][32] + bias [32]
+  for (int i = threadIdx.x; i < CLAT * kFpnC; i += blockDim.x) {
+    const int ch = i % kFpnC, ci = i / kFpnC;
+    s_latw[i] = __ldg(lat_w + (size_t)ch * CLAT + ci);
+  }
+  for (int i = threadIdx.x; i < kFpnC; i += blockDim.x) s_latw[CLAT * kFpnC + i] = __ldg(lat_b + i);
+  __syncthreads();
+  const int hi = h / 2, wi = w / 2;
+  const float sy = hi > 1 ? (float)(hi - 1) / (float)(h - 1) : 0.f;
+  const float sx = wi > 1 ? (float)(wi - 1) / (float)(w - 1) : 0.f;
+  const size_t total = (size_t)N * h * w * 4;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(t & 3);
+    const size_t pix = t >> 2;
+    const int x = (int)(pix % w);
+    const int y = (int)((pix / w) % h);
+    const int n = (int)(pix / ((size_t)w * h));
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    if (prev) {
+      const float* pn = prev + (size_t)n * hi * wi * kFpnC;
+      const float fy = sy * (float)y, fx = sx * (float)x;
+      const int ya = min((int)fy, hi - 1), xa = min((int)fx, wi - 1);
+      const int yb = min(ya + 1, hi - 1), xb = min(xa + 1, wi - 1);
+      const float ly = fy - (float)ya, lx = fx - (float)xa;
+      const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx),
+                  w11 = ly * lx;
+      const float* p00 = pn + ((size_t)ya * wi + xa) * kFpnC + g * 8;
+      const float* p01 = pn + ((size_t)ya * wi + xb) * kFpnC + g * 8;
+      const float* p10 = pn + ((size_t)yb * wi + xa) * kFpnC + g * 8;
+      const float* p11 = pn + ((size_t)yb * wi + xb) * kFpnC + g * 8;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 a = ldg4(p00 + 4 * q), b = ldg4(p01 + 4 * q), cc = ldg4(p10 + 4 * q),
+                     d = ldg4(p11 + 4 * q);
+        v[4 * q + 0] = a.x * w00 + b.x * w01 + cc.x * w10 + d.x * w11;
+        v[4 * q + 1] = a.y * w00 + b.y * w01 + cc.y * w10 + d.y * w11;
+        v[4 * q + 2] = a.z * w00 + b.z * w01 + cc.z * w10 + d.z * w11;
+        v[4 * q + 3] = a.w * w00 + b.w * w01 + cc.w * w10 + d.w * w11;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += s_latw[CLAT * kFpnC + g * 8 + k];
+    const float* cp = c + pix * CLAT;
+    for (int ci = 0; ci < CLAT; ci += 4) {
+      const float4 cv = ldg4(cp + ci);
+      const float cs[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* wr = s_latw + (ci + j) * kFpnC + g * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaf(cs[j], wr[k], v[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = round_tf32_if(v[k], round_out);
+    float* fo = feat + pix * kFpnC + g * 8;
+    st4(fo, make_float4(v[0], v[1], v[2], v[3]));
+    st4(fo + 4, make_float4(v[4], v[5], v[6], v[7]));
+  }
+}
+
+// y[n,y,x,0:8] = lrelu(conv3x3(x[n,0:3], w) + bias): planar RGB in, channels-last out.
+// One output pixel per thread; the 3x3x3 neighbourhood comes through L1 (threads of a warp
+// are consecutive in x, so every plane row is read coalesced); weights [27][8] in smem.
+__global__ void __launch_bounds__(256)
+conv2d_rgb8_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                   const float* __restrict__ bias, float slope, float* __restrict__ y, int N,
+                   int H, int W, int round_out) {
+  __shared__ __align__(16) float s_w[27 * 8 + 8];
+  for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) {
+    const int co = i & 7, r = i >> 3;            // r = ci*9 + ky*3 + kx  (torch (8,3,3,3) order)
+    s_w[i] = __ldg(w + (size_t)co * 27 + r);
+  }
+  if (threadIdx.x < 8) s_w[27 * 8 + threadIdx.x] = __ldg(bias + threadIdx.x);
+  __syncthreads();
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  const int py = blockIdx.y, n = blockIdx.z;
+  if (px >= W) return;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = s_w[27 * 8 + k];
+  const float* xn = x + (size_t)n * 3 * H * W;
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = py + ky - 1;
+      const bool yok = iy >= 0 && iy < H;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = px + kx - 1;
+        const float v = (yok && ix >= 0 && ix < W) ? __ldg(xn + ((size_t)ci * H + iy) * W + ix) : 0.f;
+        const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ci * 9 + ky * 3 + kx) * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ci * 9 + ky * 3 + kx) * 8 + 4);
+        acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+        acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+        acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+        acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float t = acc[k] >= 0.f ? acc[k] : acc[k] * slope;
+    acc[k] = round_tf32_if(t, round_out);
+  }
+  float* yo = y + (((size_t)n * H + py) * W + px) * 8;
+  st4(yo, make_float4(acc[0], acc[1], acc[2], acc[3]));
+  st4(yo + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+}
+
 // x[..., c] = lrelu(x[..., c] + bias[c]) in place on a channels-last tensor (C % 4 == 0):
 // the tail of a folded conv+ABN block when the conv itself comes from cuDNN.
 __global__ void __launch_bounds__(256)
 bias_lrelu_kernel(float* __restrict__ x, const float* __restrict__ bias, float slope, size_t n4,
-                  int C) {
+                  int C, int round_out) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const int c = (int)((i * 4) % (size_t)C);
@@ -151,6 +283,8 @@ bias_lrelu_kernel(float* __restrict__ x, const float* __restrict__ bias, float s
   v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
   v.x = v.x >= 0.f ? v.x : v.x * slope; v.y = v.y >= 0.f ? v.y : v.y * slope;
   v.z = v.z >= 0.f ? v.z : v.z * slope; v.w = v.w >= 0.f ? v.w : v.w * slope;
+  v.x = round_tf32_if(v.x, round_out); v.y = round_tf32_if(v.y, round_out);
+  v.z = round_tf32_if(v.z, round_out); v.w = round_tf32_if(v.w, round_out);
   *reinterpret_cast<float4*>(x + i * 4) = v;
 }
 
@@ -158,14 +292,20 @@ bias_lrelu_kernel(float* __restrict__ x, const float* __restrict__ bias, float s
 
 using namespace casmvs;
 
-extern "C" int casmvs_bias_lrelu_nhwc(float* x, const float* bias, float slope, size_t numel,
-                                      int C, void* stream) {
-  CASMVS_REQUIRE(x && bias, "bias_lrelu: null pointer");
-  CASMVS_REQUIRE(C > 0 && C % 4 == 0 && numel % (size_t)C == 0, "bias_lrelu: C %% 4 != 0 or ragged");
+extern "C" int casmvs_bias_act_nhwc(float* x, const float* bias, float slope, size_t numel,
+                                    int C, int round_tf32, void* stream) {
+  CASMVS_REQUIRE(x && bias, "bias_act: null pointer");
+  CASMVS_REQUIRE(C > 0 && C % 4 == 0 && numel % (size_t)C == 0, "bias_act: C %% 4 != 0 or ragged");
   if (numel == 0) return 0;
   const size_t n4 = numel / 4;
-  bias_lrelu_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, as_stream(stream)>>>(x, bias, slope, n4, C);
-  return after_launch("bias_lrelu");
+  bias_lrelu_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, as_stream(stream)>>>(
+      x, bias, slope, n4, C, round_tf32 ? 1 : 0);
+  return after_launch("bias_act");
+}
+
+extern "C" int casmvs_bias_lrelu_nhwc(float* x, const float* bias, float slope, size_t numel,
+                                      int C, void* stream) {
+  return casmvs_bias_act_nhwc(x, bias, slope, numel, C, 0, stream);
 }
 
 extern "C" int casmvs_fpn_level_fwd(const float* prev, const float* c, const float* lat_w,
@@ -191,4 +331,34 @@ extern "C" int casmvs_fpn_level_fwd(const float* prev, const float* c, const flo
     fpn_level_kernel<16><<<grd, 256, smem, st>>>(prev, c, lat_w, lat_b, smooth_w, smooth_b, feat_out, out, h, w, CLAT);
   }
   return after_launch("fpn_level");
+}
+
+extern "C" int casmvs_fpn_merge_fwd(const float* prev, const float* c, const float* lat_w,
+                                    const float* lat_b, float* feat, int N, int h, int w,
+                                    int CLAT, int round_tf32, void* stream) {
+  CASMVS_REQUIRE(c && lat_w && lat_b && feat, "fpn_merge: null pointer");
+  CASMVS_REQUIRE(N >= 0 && h >= 1 && w >= 1, "fpn_merge: bad dims");
+  CASMVS_REQUIRE(!prev || (h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0),
+                 "fpn_merge: h,w must be even when a coarser level is upsampled");
+  CASMVS_REQUIRE(CLAT % 4 == 0 && CLAT > 0 && CLAT <= 64, "fpn_merge: CLAT must be a multiple of 4");
+  if (N == 0) return 0;
+  const size_t total = (size_t)N * h * w * 4;
+  const size_t want = (total + 255) / 256;
+  const unsigned blocks = (unsigned)(want < (size_t)num_sms() * 16 ? want : (size_t)num_sms() * 16);
+  const size_t smem = (size_t)(CLAT * kFpnC + kFpnC) * 4;
+  fpn_merge_kernel<<<blocks, 256, smem, as_stream(stream)>>>(prev, c, lat_w, lat_b, feat, N, h, w,
+                                                            CLAT, round_tf32 ? 1 : 0);
+  return after_launch("fpn_merge");
+}
+
+extern "C" int casmvs_conv2d_rgb8_fwd(const float* x, const float* w, const float* bias,
+                                      float slope, float* y, int N, int H, int W,
+                                      int round_tf32, void* stream) {
+  CASMVS_REQUIRE(x && w && bias && y, "conv2d_rgb8: null pointer");
+  CASMVS_REQUIRE(N >= 0 && N <= 65535 && H >= 1 && H <= 65535 && W >= 1, "conv2d_rgb8: bad dims");
+  if (N == 0) return 0;
+  dim3 grd((W + 127) / 128, H, N);
+  conv2d_rgb8_kernel<<<grd, 128, 0, as_stream(stream)>>>(x, w, bias, slope, y, N, H, W,
+                                                         round_tf32 ? 1 : 0);
+  return after_launch("conv2d_rgb8");
 }

@@ -42,6 +42,10 @@ class FeatureNet(nn.Module):
     # cuDNN would run fp32 convs as TF32 on B200 by default; the reference path is fp32
     # (opt.py:69-70), so IEEE fp32 is kept unless the model runs in its tf32 precision mode.
     allow_tf32 = False
+    # tf32 precision mode, inference: the 3x3 stride-1 convs run on tcgen05 as planar (1x3x3)
+    # convolutions over the (views, H, W) volume, the first block and the top-down merges in
+    # this library's own kernels; only the two 5x5 stride-2 convs stay with cuDNN
+    tensor_path = True
     # the reference's inference script turns cuDNN autotuning on (eval.py:19); without it
     # cuDNN's heuristics pick FFT/sgemm algorithms that are several times slower here
     benchmark = True
@@ -51,6 +55,8 @@ class FeatureNet(nn.Module):
                                         allow_tf32=self.allow_tf32):
             if self.training or torch.is_grad_enabled():
                 return self._forward_modules(x)
+            if self.allow_tf32 and self.tensor_path and x.is_cuda:
+                return self._forward_tensor(x)
             return self._forward_folded(x)
 
     # -- inference path: eval-mode ABN folded into the conv (w*alpha, beta') so each block
@@ -70,6 +76,50 @@ class FeatureNet(nn.Module):
                               activation_slope(b.bn)))
             self._fold_cache, self._fold_key = cache, key
         return self._fold_cache
+
+    # -- tf32 inference path (see `tensor_path`)
+    def _packed(self):
+        cache = self._folded()
+        key = self._fold_key
+        if getattr(self, "_pack_key", None) != key:
+            packed = {}
+            for i in (1, 3, 4, 6, 7):               # the 3x3 stride-1 blocks
+                w = cache[i][0]
+                packed[i] = ops.pack_conv3d_weight(w.contiguous(), ops.CONV_PLANAR)
+            self._pack_cache, self._pack_key = packed, key
+        skey = tuple((t.data_ptr(), t._version) for t in (self.smooth0.weight, self.smooth1.weight))
+        if getattr(self, "_smooth_key", None) != skey:
+            self._smooth_pack = (ops.pack_conv3d_weight(self.smooth0.weight.detach(), ops.CONV_PLANAR),
+                                 ops.pack_conv3d_weight(self.smooth1.weight.detach(), ops.CONV_PLANAR))
+            self._smooth_key = skey
+        return cache, self._pack_cache, self._smooth_pack
+
+    def _forward_tensor(self, x):
+        cache, packed, (sm0, sm1) = self._packed()
+
+        def planar(t, i, keep):
+            w, b, _, _, slope = cache[i]
+            return ops.conv2d_planar(t, packed[i], w.shape[1], w.shape[0], b, slope, ops.TF32,
+                                     keep_fp32=keep)
+
+        def strided(t, i):
+            w, b, stride, pad, slope = cache[i]
+            t = F.conv2d(t, w, None, stride, pad)
+            if not t.is_contiguous(memory_format=torch.channels_last):
+                t = t.contiguous(memory_format=torch.channels_last)
+            return ops.bias_lrelu_(t, b, slope, round_tf32=True)
+
+        w0, b0, _, _, slope0 = cache[0]
+        t = ops.conv2d_rgb8(x, w0, b0, slope0, round_tf32=True)
+        c0 = planar(t, 1, True)                       # consumers: cuDNN conv + lateral (fp32)
+        c1 = planar(planar(strided(c0, 2), 3, False), 4, True)
+        c2 = planar(planar(strided(c1, 5), 6, False), 7, True)
+        f2 = ops.fpn_merge(None, c2, self.toplayer.weight, self.toplayer.bias)
+        m1 = ops.fpn_merge(f2, c1, self.lat1.weight, self.lat1.bias, round_tf32=True)
+        m0 = ops.fpn_merge(m1, c0, self.lat0.weight, self.lat0.bias, round_tf32=True)
+        l1 = ops.conv2d_planar(m1, sm1, 32, 16, self.smooth1.bias, 1.0, ops.TF32, keep_fp32=True)
+        l0 = ops.conv2d_planar(m0, sm0, 32, 8, self.smooth0.bias, 1.0, ops.TF32, keep_fp32=True)
+        return {"level_0": l0, "level_1": l1, "level_2": f2}
 
     def _forward_folded(self, x):
         x = x.contiguous(memory_format=torch.channels_last)

@@ -11,7 +11,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (CONV, CONV_TRANSPOSE, FP32, NCHW, NHWC, PRECISIONS, TF32,  # noqa: F401
+from ._lib import (CONV, CONV_PLANAR, CONV_TRANSPOSE, FP32, KEEP_FP32_OUT, NCHW, NHWC, PRECISIONS, TF32,  # noqa: F401
                    TF32X3, check)
 
 _checked_devices = set()
@@ -35,7 +35,10 @@ def _require_cuda(*tensors):
                 f"got a tensor on {t.device}")
         if t.dtype != torch.float32:
             raise _lib.CasMVSError(f"fp32 only (reference opt.py:69-70), got {t.dtype}")
-    dev = tensors[0].device.index
+    first = next((t for t in tensors if t is not None), None)
+    if first is None:
+        return
+    dev = first.device.index
     if dev is None:
         dev = torch.cuda.current_device()
     if dev not in _checked_devices:
@@ -139,10 +142,13 @@ def invalidate_weight_cache():
 
 
 def pack_conv3d_weight(weight, kind):
-    """torch Conv3d (Cout,Cin,3,3,3) / ConvTranspose3d (Cin,Cout,3,3,3) -> [27][Cin][Cout]."""
+    """torch Conv3d (Cout,Cin,3,3,3) / ConvTranspose3d (Cin,Cout,3,3,3) / Conv2d (Cout,Cin,3,3)
+    [kind CONV_PLANAR: centre plane of a 1x3x3 kernel] -> [27][Cin][Cout]."""
     _require_cuda(weight)
     invalidate_weight_cache()
-    if kind == CONV:
+    if kind == CONV_PLANAR:
+        assert weight.dim() == 4 and tuple(weight.shape[2:]) == (3, 3)
+    if kind in (CONV, CONV_PLANAR):
         cout, cin = weight.shape[:2]
     else:
         cin, cout = weight.shape[:2]
@@ -159,7 +165,10 @@ def conv3d(x, w_packed, cin, cout, scale=None, shift=None, slope=1.0, skip=None,
     _no_grad_only(x)
     xs = volume_storage(x)
     B, D, h, w, _ = xs.shape
-    if kind == CONV:
+    if kind == CONV_PLANAR:
+        assert stride == 1
+        Do, ho, wo = D, h, w
+    elif kind == CONV:
         Do, ho, wo = (D - 1) // stride + 1, (h - 1) // stride + 1, (w - 1) // stride + 1
     else:
         Do, ho, wo = 2 * D, 2 * h, 2 * w
@@ -283,10 +292,66 @@ def fpn_level(prev, c, lat_w, lat_b, smooth_w, smooth_b, want_feat):
     return feat, out
 
 
-def bias_lrelu_(x, bias, slope):
-    """In-place LeakyReLU(x + bias[c]) on a channels-last (N,C,h,w) tensor."""
+def conv2d_planar(x, w_packed, cin, cout, shift=None, slope=1.0, precision=TF32,
+                  keep_fp32=False, scale=None):
+    """3x3 Conv2d (pad 1) + per-channel scale/shift + LeakyReLU over a channels-last
+    (N,Cin,H,W) batch, run as ONE 1x3x3 convolution over the (N,H,W) volume
+    (casmvs_conv3d_fwd, kind CONV_PLANAR).  Returns (N,Cout,H,W) channels-last."""
+    _require_cuda(x, w_packed, scale, shift)
+    _no_grad_only(x)
+    xs = x.contiguous(memory_format=torch.channels_last)
+    N, C, H, W = xs.shape
+    assert C == cin
+    y = torch.empty((N, cout, H, W), device=x.device, dtype=torch.float32,
+                    memory_format=torch.channels_last)
+    check(_lib.load().casmvs_conv3d_fwd(_ptr(xs), _ptr(w_packed), _ptr(scale), _ptr(shift),
+                                        float(slope), None, _ptr(y), 1, cin, cout, N, H, W,
+                                        CONV_PLANAR, 1,
+                                        precision | (KEEP_FP32_OUT if keep_fp32 else 0),
+                                        _stream()), "conv2d_planar")
+    return y
+
+
+def fpn_merge(prev, c, lat_w, lat_b, round_tf32=False):
+    """upsample_x2(prev) + conv1x1(c) + bias -> (N,32,h,w) channels-last (prev None: the
+    lateral alone, i.e. FeatureNet.toplayer).  models/mvsnet.py:36-47."""
+    _require_cuda(prev, c, lat_w, lat_b)
+    cv = c.contiguous(memory_format=torch.channels_last)
+    N, clat, h, w = cv.shape
+    pv = None
+    if prev is not None:
+        pv = prev.contiguous(memory_format=torch.channels_last)
+        assert pv.shape == (N, 32, h // 2, w // 2)
+    assert lat_w.shape[0] == 32 and lat_w.shape[1] == clat
+    feat = torch.empty((N, 32, h, w), device=c.device, dtype=torch.float32,
+                       memory_format=torch.channels_last)
+    check(_lib.load().casmvs_fpn_merge_fwd(_ptr(pv), _ptr(cv), _ptr(lat_w.detach().contiguous()),
+                                           _ptr(lat_b.detach().contiguous()), _ptr(feat), N, h, w,
+                                           clat, 1 if round_tf32 else 0, _stream()), "fpn_merge")
+    return feat
+
+
+def conv2d_rgb8(x, w, bias, slope, round_tf32=False):
+    """First FeatureNet block with folded ABN: planar (N,3,H,W) images -> (N,8,H,W)
+    channels-last.  w (8,3,3,3) torch layout."""
+    _require_cuda(x, w, bias)
+    xs = x.contiguous()
+    N, C, H, W = xs.shape
+    assert C == 3 and tuple(w.shape) == (8, 3, 3, 3)
+    y = torch.empty((N, 8, H, W), device=x.device, dtype=torch.float32,
+                    memory_format=torch.channels_last)
+    check(_lib.load().casmvs_conv2d_rgb8_fwd(_ptr(xs), _ptr(w.contiguous()), _ptr(bias),
+                                             float(slope), _ptr(y), N, H, W,
+                                             1 if round_tf32 else 0, _stream()), "conv2d_rgb8")
+    return y
+
+
+def bias_lrelu_(x, bias, slope, round_tf32=False):
+    """In-place LeakyReLU(x + bias[c]) on a channels-last (N,C,h,w) tensor (optionally stored
+    TF32-rounded for a tensor-core consumer)."""
     _require_cuda(x, bias)
     assert x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] % 4 == 0
-    check(_lib.load().casmvs_bias_lrelu_nhwc(_ptr(x), _ptr(bias), float(slope), x.numel(),
-                                             x.shape[1], _stream()), "bias_lrelu")
+    check(_lib.load().casmvs_bias_act_nhwc(_ptr(x), _ptr(bias), float(slope), x.numel(),
+                                           x.shape[1], 1 if round_tf32 else 0, _stream()),
+          "bias_lrelu")
     return x

@@ -52,9 +52,21 @@ enum casmvs_precision {
   CASMVS_TF32X3 = 2 /* error-compensated 3xTF32 split (fp32-equivalent)      */
 };
 
+/* OR-ed into casmvs_conv3d_fwd's precision: store the output unrounded even in the TF32
+ * mode (by default activations are stored TF32-rounded there because the next tensor-core
+ * layer would otherwise truncate them; the last layer before a non-tensor consumer should
+ * keep the fp32 accumulator). */
+#define CASMVS_KEEP_FP32_OUT 256
+
 enum casmvs_conv_kind {
-  CASMVS_CONV = 0,          /* Conv3d(k=3, pad=1, stride 1|2)   modules.py:26      */
-  CASMVS_CONV_TRANSPOSE = 1 /* ConvTranspose3d(k=3,s=2,p=1,op=1) mvsnet.py:75,80,85 */
+  CASMVS_CONV = 0,           /* Conv3d(k=3, pad=1, stride 1|2)   modules.py:26      */
+  CASMVS_CONV_TRANSPOSE = 1, /* ConvTranspose3d(k=3,s=2,p=1,op=1) mvsnet.py:75,80,85 */
+  /* 1x3x3 kernel, stride 1, pad (0,1,1): the 3x3 Conv2d layers of FeatureNet
+   * (ConvBnReLU modules.py:8-18, smooth0/1 mvsnet.py:30-31) run as ONE convolution over
+   * the (views, H, W) volume of a batch.  Packed weights keep the [27][Cin][Cout] layout
+   * with zero kd = 0 and kd = 2 planes, so every K2 kernel computes it correctly and the
+   * tensor-core kernels skip the two empty planes. */
+  CASMVS_CONV_PLANAR = 2
 };
 
 /* ---- library / device ------------------------------------------------- */
@@ -101,9 +113,11 @@ int casmvs_homo_warp_fwd(const float* src_feat, int feat_layout, const float* pr
  * casmvs_pack_conv3d_weights (tap-major [27][Cin][Cout]).
  * For kind == CASMVS_CONV: stride in {1,2}, out dims = (in-1)/stride+1.
  * For kind == CASMVS_CONV_TRANSPOSE: out dims = 2*in.
+ * For kind == CASMVS_CONV_PLANAR: stride 1, out dims = in dims.
  */
 size_t casmvs_packed_conv3d_weight_floats(int Cin, int Cout);
-/* w_torch: Conv3d layout (Cout,Cin,3,3,3) or ConvTranspose3d layout (Cin,Cout,3,3,3) */
+/* w_torch: Conv3d layout (Cout,Cin,3,3,3), ConvTranspose3d layout (Cin,Cout,3,3,3) or, for
+ * CASMVS_CONV_PLANAR, Conv2d layout (Cout,Cin,3,3) */
 int casmvs_pack_conv3d_weights(const float* w_torch, int kind, int Cin, int Cout,
                                float* w_packed, void* stream);
 /* The tensor-core kernels keep a per-process cache of operand images keyed by the
@@ -171,10 +185,30 @@ int casmvs_fpn_level_fwd(const float* prev, const float* c, const float* lat_w,
                          float* feat_out, float* out, int N, int h, int w, int CLAT, int COUT,
                          void* stream);
 
+/* The same level split in two for the tensor-core path: this call produces
+ *   feat = upsample_x2_bilinear(prev, align_corners=True) + conv1x1(c, lat_w) + lat_b
+ * (N,h,w,32), optionally TF32-rounded, and the 3x3 smooth runs as a CASMVS_CONV_PLANAR
+ * casmvs_conv3d_fwd on tcgen05.  prev == NULL: feat = conv1x1(c) + lat_b (the `toplayer`,
+ * mvsnet.py:27,41).  lat_w (32,CLAT[,1,1]) torch layout; CLAT % 4 == 0. */
+int casmvs_fpn_merge_fwd(const float* prev, const float* c, const float* lat_w,
+                         const float* lat_b, float* feat, int N, int h, int w, int CLAT,
+                         int round_tf32, void* stream);
+
+/* First FeatureNet block (ConvBnReLU(3, 8, 3, 1, 1), mvsnet.py:13 + modules.py:8-18) with the
+ * eval-mode ABN folded: y = LeakyReLU(conv3x3(x, w, pad 1) + bias).  x (N,3,H,W) planar fp32
+ * (the image batch as the data loader hands it over, no re-layout), w (8,3,3,3) torch
+ * layout already multiplied by the ABN scale, y (N,H,W,8) channels-last. */
+int casmvs_conv2d_rgb8_fwd(const float* x, const float* w, const float* bias, float slope,
+                           float* y, int N, int H, int W, int round_tf32, void* stream);
+
 /* In-place x[...,c] = LeakyReLU(x[...,c] + bias[c]) on a channels-last tensor (C % 4 == 0):
  * the epilogue of a folded conv + eval-mode ABN block (models/modules.py:8-18). */
 int casmvs_bias_lrelu_nhwc(float* x, const float* bias, float slope, size_t numel, int C,
                            void* stream);
+/* Same, optionally storing the result TF32-rounded (round to nearest) for a tensor-core
+ * consumer that would otherwise truncate it. */
+int casmvs_bias_act_nhwc(float* x, const float* bias, float slope, size_t numel, int C,
+                         int round_tf32, void* stream);
 
 /* ---- layout helpers ------------------------------------------------------ */
 /* (N,C,S) -> (N,S,C) and back, S = product of spatial dims. */

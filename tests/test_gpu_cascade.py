@@ -139,6 +139,23 @@ def test_feature_net_channels_last_matches_oracle():
         assert (f[k].cpu() - ref[k]).abs().max() < 5e-2
 
 
+def test_feature_net_tensor_path_matches_fp32_path():
+    """tf32 mode: 3x3 convs as planar tcgen05 convolutions + own first block / merges, against
+    the fp32 cuDNN path of the same model (10-bit operand mantissas through 8 conv layers)."""
+    model, sd = build(1, "tf32")
+    x = torch.randn(3, 3, 128, 160)
+    with torch.no_grad():
+        f = model.feature(x.to(DEV))
+        model.set_precision("fp32")
+        ref = model.feature(x.to(DEV))
+    for k in ref:
+        assert ops.is_channels_last_feats(f[k]) and f[k].shape == ref[k].shape
+        scale = ref[k].abs().max().item()
+        err = (f[k] - ref[k]).abs()
+        print(k, "max", err.max().item() / scale, "mean", err.mean().item() / scale)
+        assert err.max().item() < 1e-2 * scale and err.mean().item() < 1e-3 * scale
+
+
 def test_graph_and_pipeline_match_eager():
     """CUDA-graph replay and the 2-slot host-buffer pipeline give bit-identical results to
     eager calls (same kernels, same order per view)."""

@@ -301,6 +301,68 @@ def test_fused_fpn_level_vs_torch_cpu(clat, cout, hw):
     assert ops.is_channels_last_feats(got)
 
 
+@pytest.mark.parametrize("clat,hw,with_prev", [(16, (20, 28), True), (8, (34, 50), True),
+                                               (32, (9, 13), False)])
+def test_fpn_merge_vs_torch_cpu(clat, hw, with_prev):
+    """csrc/fpn.cu fpn_merge_kernel == up2(prev) + lat(c) (models/mvsnet.py:36-47), fp32."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(clat + 7)
+    h, w = hw
+    prev = torch.randn(2, 32, h // 2, w // 2, generator=g) if with_prev else None
+    c = torch.randn(2, clat, h, w, generator=g)
+    lat_w = torch.randn(32, clat, 1, 1, generator=g) * 0.2
+    lat_b = torch.randn(32, generator=g) * 0.1
+    want = F.conv2d(c, lat_w, lat_b)
+    if with_prev:
+        want = want + F.interpolate(prev, scale_factor=2, mode="bilinear", align_corners=True)
+    got = ops.fpn_merge(prev.to(DEV) if with_prev else None, c.to(DEV), lat_w.to(DEV), lat_b.to(DEV))
+    assert stats(f"fpn_merge clat={clat}", got.cpu(), want).max() < 2e-5
+    assert ops.is_channels_last_feats(got)
+    got_r = ops.fpn_merge(prev.to(DEV) if with_prev else None, c.to(DEV), lat_w.to(DEV),
+                          lat_b.to(DEV), round_tf32=True).cpu()
+    assert (got_r - want).abs().max() < 2.0 ** -11 * want.abs().max() + 2e-5
+    assert torch.equal(got_r.view(torch.int32) & 0x1FFF, torch.zeros_like(got_r, dtype=torch.int32))
+
+
+def test_conv2d_rgb8_vs_torch_cpu():
+    """First FeatureNet block (ConvBnReLU(3,8,3,1,1) with folded ABN) from planar images."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(3, 3, 37, 141, generator=g)
+    w = torch.randn(8, 3, 3, 3, generator=g) * 0.3
+    b = torch.randn(8, generator=g) * 0.1
+    want = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
+    got = ops.conv2d_rgb8(x.to(DEV), w.to(DEV), b.to(DEV), 0.01)
+    assert stats("conv2d_rgb8", got.cpu(), want).max() < 1e-5
+    assert ops.is_channels_last_feats(got)
+
+
+@pytest.mark.parametrize("cin,cout,hw", [(8, 8, (37, 61)), (16, 16, (40, 24)), (32, 32, (18, 30)),
+                                         (32, 16, (33, 47)), (32, 8, (64, 90))])
+def test_planar_conv_tensor_core_vs_torch_cpu(cin, cout, hw):
+    """The 3x3 Conv2d layers of FeatureNet as a CONV_PLANAR (1x3x3) convolution over the
+    (views, H, W) volume on tcgen05, against torch fp32 on the CPU; and the CUDA-core kernel
+    running the same packed weights (zero outer planes) in fp32."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(5, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) * 0.1
+    b = torch.randn(cout, generator=g) * 0.1
+    want = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
+    wp = ops.pack_conv3d_weight(w.to(DEV), ops.CONV_PLANAR)
+    xs = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    ref = ops.conv2d_planar(xs, wp, cin, cout, b.to(DEV), 0.01, ops.FP32)
+    assert stats(f"planar fp32 {cin}->{cout}", ref.cpu(), want).max() < 5e-5
+    got = ops.conv2d_planar(xs, wp, cin, cout, b.to(DEV), 0.01, ops.TF32, keep_fp32=True)
+    err = stats(f"planar tf32 {cin}->{cout}", got.cpu(), want)
+    assert err.max() < 1.5e-3 * want.abs().max().item()
+    assert ops.is_channels_last_feats(got)
+    rounded = ops.conv2d_planar(xs, wp, cin, cout, b.to(DEV), 0.01, ops.TF32).cpu()
+    assert torch.equal(rounded.view(torch.int32) & 0x1FFF,
+                       torch.zeros_like(rounded, dtype=torch.int32))
+    assert (rounded - got.cpu()).abs().max() <= 2.0 ** -11 * got.abs().max().item()
+
+
 # ----------------------------------------------------------------------------- K2 on tcgen05
 @pytest.mark.parametrize("kind,cin,cout,dims", [
     ("conv1", 8, 8, (5, 20, 13)), ("conv1", 16, 8, (16, 40, 24)), ("conv1", 32, 8, (8, 32, 40)),
