@@ -37,6 +37,10 @@ int conv3d_tma_n8(const float* x, const float* wpk, const float* scale, const fl
 int conv3d_tc3(const float* x, const float* wpk, const float* scale, const float* shift,
                float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
                int w, int kind, int stride, int precision, cudaStream_t st);
+// conv3d_tma2.cu (tcgen05 + TMA producer, persistent: stride-2 and transposed layers)
+int conv3d_tma2(const float* x, const float* wpk, const float* scale, const float* shift,
+                float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
+                int w, int kind, int stride, int precision, cudaStream_t st);
 // conv3d_tc2.cu (tcgen05, stride-2 and transposed layers)
 int conv3d_tc2(const float* x, const float* wpk, const float* scale, const float* shift,
                float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
@@ -124,6 +128,9 @@ extern "C" int casmvs_conv3d_fwd(const float* x, const float* w_packed, const fl
     if (kind != CASMVS_CONV_PLANAR) {
       rc = conv3d_tc(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
                      stride, precision, st);
+      if (rc <= 0) return rc;
+      rc = conv3d_tma2(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
+                       stride, precision, st);
       if (rc <= 0) return rc;
       rc = conv3d_tc2(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
                       stride, precision, st);

@@ -315,16 +315,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 
 // Tensor maps are pure functions of (pointer, shape, box): memoised, since inference calls
 // every layer with the same workspace pointers each step.
-struct MapEntry { const void* x; int B, D, H, W, C, CB, bw, bh; CUtensorMap map; };
+struct MapEntry { const void* x; int B, D, H, W, C, CB, bw, bh, sw; CUtensorMap map; };
 static MapEntry g_maps[128];
 static int g_maps_n = 0, g_maps_next = 0;
 
 const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, int C, int CB, int box_w,
-                             int box_h) {
+                             int box_h, int stride_w) {
   for (int i = 0; i < g_maps_n; ++i) {
     const MapEntry& e = g_maps[i];
     if (e.x == x && e.B == B && e.D == D && e.H == H && e.W == W && e.C == C && e.CB == CB &&
-        e.bw == box_w && e.bh == box_h)
+        e.bw == box_w && e.bh == box_h && e.sw == stride_w)
       return &e.map;
   }
   auto enc = encode_fn();
@@ -337,7 +337,7 @@ const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, int C, 
   const cuuint64_t gstr[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4,
                               (cuuint64_t)D * H * W * C * 4};
   const cuuint32_t box[5] = {(cuuint32_t)CB, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const cuuint32_t estr[5] = {1, (cuuint32_t)stride_w, 1, 1, 1};
   const CUtensorMapSwizzle sw = CB * 4 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : CB * 4 == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -350,7 +350,7 @@ const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, int C, 
               (int)r, C, W, H, D, B);
     return nullptr;
   }
-  e.x = x; e.B = B; e.D = D; e.H = H; e.W = W; e.C = C; e.CB = CB; e.bw = box_w; e.bh = box_h;
+  e.x = x; e.B = B; e.D = D; e.H = H; e.W = W; e.C = C; e.CB = CB; e.bw = box_w; e.bh = box_h; e.sw = stride_w;
   return &e.map;
 }
 

@@ -166,14 +166,12 @@ fpn_merge_kernel(const float* __restrict__ prev,   // (N, h/2, w/2, 32) or null
   const int hi = h / 2, wi = w / 2;
   const float sy = hi > 1 ? (float)(hi - 1) / (float)(h - 1) : 0.f;
   const float sx = wi > 1 ? (float)(wi - 1) / (float)(w - 1) : 0.f;
-  const size_t total = (size_t)N * h * w * 4;
-  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (size_t)gridDim.x * blockDim.x) {
-    const int g = (int)(t & 3);
-    const size_t pix = t >> 2;
-    const int x = (int)(pix % w);
-    const int y = (int)((pix / w) % h);
-    const int n = (int)(pix / ((size_t)w * h));
+  // one (row, image) per blockIdx.y/z: no 64-bit index arithmetic in the loop
+  const int y = blockIdx.y, n = blockIdx.z;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < w * 4; t += gridDim.x * blockDim.x) {
+    const int g = t & 3;
+    const int x = t >> 2;
+    const size_t pix = ((size_t)n * h + y) * w + x;
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = 0.f;
@@ -342,10 +340,9 @@ extern "C" int casmvs_fpn_merge_fwd(const float* prev, const float* c, const flo
                  "fpn_merge: h,w must be even when a coarser level is upsampled");
   CASMVS_REQUIRE(CLAT % 4 == 0 && CLAT > 0 && CLAT <= 64, "fpn_merge: CLAT must be a multiple of 4");
   if (N == 0) return 0;
-  const size_t total = (size_t)N * h * w * 4;
-  const size_t want = (total + 255) / 256;
-  const unsigned blocks = (unsigned)(want < (size_t)num_sms() * 16 ? want : (size_t)num_sms() * 16);
+  CASMVS_REQUIRE(N <= 65535 && h <= 65535, "fpn_merge: N, h must be <= 65535");
   const size_t smem = (size_t)(CLAT * kFpnC + kFpnC) * 4;
+  dim3 blocks((w * 4 + 255) / 256, h, N);
   fpn_merge_kernel<<<blocks, 256, smem, as_stream(stream)>>>(prev, c, lat_w, lat_b, feat, N, h, w,
                                                             CLAT, round_tf32 ? 1 : 0);
   return after_launch("fpn_merge");

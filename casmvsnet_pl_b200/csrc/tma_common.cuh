@@ -23,10 +23,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
 
 // Tiled tensor map over the activation tensor x (B,D,H,W,C) viewed as {C, W, H, D, B} with box
 // {CB, box_w, box_h, 1, 1}, swizzle = CB*4 bytes (128/64/32), out-of-bounds elements zero-filled
-// (= the convolution's zero padding).  Memoised by (pointer, shape, box); null + casmvs error
-// when the driver entry point is missing or the encode fails.  (conv3d_tma.cu)
+// (= the convolution's zero padding).  stride_w = 2: the box walks every second voxel along W
+// (box_w counts traversed positions, so ceil(box_w / 2) voxels are loaded): the even / odd
+// column planes of the stride-2 convolutions.  Memoised by (pointer, shape, box); null +
+// casmvs error when the driver entry point is missing or the encode fails.  (conv3d_tma.cu)
 const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, int C, int CB, int box_w,
-                             int box_h);
+                             int box_h, int stride_w = 1);
 
 inline int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
 

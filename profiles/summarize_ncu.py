@@ -23,7 +23,7 @@ def launches(path):
         print(f"{v/1e3:10.1f} us {c:4d}x {100*v/tot:5.1f}%  {n}")
     print("## in launch order (this repo's kernels)")
     for n, v, g in rows:
-        if any(k in n for k in ("casmvs", "tc::", "tc2::", "tc3::", "tma::", "tma8::")):
+        if any(k in n for k in ("casmvs", "tc::", "tc2::", "tc3::", "tma::", "tma8::", "tma2::")):
             print(f"{v/1e3:9.1f} us {g:>16s}  {re.sub(r'\(.*', '', n)[:80]}")
 
 def full(path):
