@@ -36,8 +36,8 @@ using namespace casmvs::tc;
 using casmvs::tma::mbar_expect_tx;
 using casmvs::tma::tma_load_5d;
 
-constexpr int kThreads8 = 6 * 32;
-constexpr int kProdWarp = 4, kIssueWarp = 5;
+// warps: SETS x 4 epilogue warps (set k drains the output slices j with j % SETS == k; warp w of
+// any set reads TMEM lanes 32*(w % 4)..), then the TMA producer warp, then the MMA issuer
 constexpr int kRowsOut = 4;     // image rows per tile (= epilogue warps)
 constexpr int kBH = 6;          // brick rows (with halo)
 constexpr int kBW = 32;         // brick columns (with halo) = lanes of a warp
@@ -106,11 +106,13 @@ __device__ __forceinline__ void tmem_zero8(uint32_t taddr) {
                : "memory");
 }
 
-template <int CIN, int SLOTS_>
-__global__ void __launch_bounds__(kThreads8, 1)
+template <int CIN, int SLOTS_, int SETS>
+__global__ void __launch_bounds__((4 * SETS + 2) * 32, 1)
 conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   using S = Smem<CIN, SLOTS_>;
   constexpr int SLOTS = S::SLOTS;
+  constexpr int kThreads8 = (4 * SETS + 2) * 32;
+  constexpr int kProdWarp = 4 * SETS, kIssueWarp = 4 * SETS + 1;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t s_raw = smem_u32(smem_raw);
   const uint32_t s_base = (s_raw + 1023u) & ~1023u;
@@ -246,11 +248,12 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
         umma_commit(bar_tfull + 8 * j, elected);
       }
     } else {
-      // ===================== epilogue warps 0..3: one image row each =====================
-      const int oh = h0 + warp, ow = w0 + lane;
+      // ============ epilogue warps: one image row each, set (warp / 4) of SETS ============
+      const int q = warp & 3, set = warp >> 2;
+      const int oh = h0 + q, ow = w0 + lane;
       const bool writes = lane < kColsOut && oh < p.H && ow < p.W;
-      const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
-      for (int j = 0; j < p.dchunk; ++j) {
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int j = set; j < p.dchunk; j += SETS) {
         if (threadIdx.x == 0) N8_STAMP(2, ep * p.dchunk + j, 0);
         mbar_wait(bar_tfull + 8 * j, ep & 1);
         if (threadIdx.x == 0) N8_STAMP(2, ep * p.dchunk + j, 1);
@@ -351,10 +354,11 @@ __global__ void build_image_n8_kernel(const float* __restrict__ wpk, float* __re
   }
 }
 
-template <int CIN, int SLOTS>
+template <int CIN, int SLOTS, int SETS>
 static int launch8(const float* x, const float* wpk, Params p, cudaStream_t st) {
   using S = Smem<CIN, SLOTS>;
-  auto kfn = conv3d_tma_n8_kernel<CIN, SLOTS>;
+  constexpr int kThreads8 = (4 * SETS + 2) * 32;
+  auto kfn = conv3d_tma_n8_kernel<CIN, SLOTS, SETS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -379,7 +383,17 @@ static int launch8(const float* x, const float* wpk, Params p, cudaStream_t st) 
   // system), at most 4.  Measured on cfg2 (profiles/r1_n8_per_sm.txt): more, shorter-chunk CTAs
   // beat fewer, longer ones for Cin = 8 and 16 (the epilogue's store latency is what has to be
   // hidden); Cin = 32 fits two.
-  const int smem_limit = (228 * 1024) / (S::kTotal + 1024);
+  // resident CTAs by shared memory (1 KB per CTA is reserved by the system) and registers
+  static int reg_limit = 0;
+  if (!reg_limit) {
+    cudaFuncAttributes fa;
+    reg_limit = 4;
+    if (cudaFuncGetAttributes(&fa, kfn) == cudaSuccess && fa.numRegs > 0)
+      reg_limit = 65536 / (((fa.numRegs + 7) / 8 * 8) * kThreads8);
+    if (reg_limit < 1) reg_limit = 1;
+  }
+  int smem_limit = (228 * 1024) / (S::kTotal + 1024);
+  if (smem_limit > reg_limit) smem_limit = reg_limit;
   int per_sm = smem_limit < 4 ? smem_limit : 4;
   if (per_sm_env > 0 && per_sm_env < per_sm) per_sm = per_sm_env;
   if (per_sm < 1) per_sm = 1;
@@ -438,9 +452,19 @@ int conv3d_tma_n8(const float* x, const float* wpk, const float* scale, const fl
   p.planar = kind == CASMVS_CONV_PLANAR ? 1 : 0;
   // the prob head feeds the softmax: keep fp32; callers can ask for unrounded outputs
   p.round_out = (round_out && Cout > 1 && !(precision_flags & CASMVS_KEEP_FP32_OUT)) ? 1 : 0;
-  if (Cin == 8) return tma8::launch8<8, 4>(x, wpk, p, st);
-  if (Cin == 16) return tma8::launch8<16, 4>(x, wpk, p, st);
-  return tma8::launch8<32, 3>(x, wpk, p, st);
+  static int sets = -1;
+  if (sets < 0) {
+    const char* e = getenv("CASMVS_N8_SETS");
+    sets = e ? atoi(e) : 1;
+  }
+  if (sets == 2) {
+    if (Cin == 8) return tma8::launch8<8, 4, 2>(x, wpk, p, st);
+    if (Cin == 16) return tma8::launch8<16, 4, 2>(x, wpk, p, st);
+    return tma8::launch8<32, 3, 2>(x, wpk, p, st);
+  }
+  if (Cin == 8) return tma8::launch8<8, 4, 1>(x, wpk, p, st);
+  if (Cin == 16) return tma8::launch8<16, 4, 1>(x, wpk, p, st);
+  return tma8::launch8<32, 3, 1>(x, wpk, p, st);
 }
 
 }  // namespace casmvs

@@ -146,9 +146,12 @@ __device__ __forceinline__ float round_tf32_if(float x, int on) {
 }
 
 // feat[n,y,x,:] = up2_bilinear(prev)[n,y,x,:] + lat_w @ c[n,y,x,:] + lat_b  (32 channels).
-// Four threads per pixel, 8 channels each: 4 x 32 B of `prev` per bilinear corner, the pixel's
-// CLAT lateral inputs (shared by the four threads through L1), one 32 B store.  HBM-bound:
-// reads c + prev (a quarter of the pixels), writes 128 B per pixel.
+// Four threads per pixel (8 channels each) x kMergeP pixels per thread.  The kernel is bound
+// by the L1/shared pipe (ncu: l1tex 89 % with one pixel per thread, profiles/r1_misc_full):
+// every 128-bit shared or global access costs a warp four L1 cycles, so the lateral weights
+// of a channel group are read from shared memory once per kMergeP pixels instead of once per
+// pixel.  HBM traffic: reads c + prev (a quarter of the pixels), writes 128 B per pixel.
+constexpr int kMergeP = 4;
 __global__ void __launch_bounds__(256)
 fpn_merge_kernel(const float* __restrict__ prev,   // (N, h/2, w/2, 32) or null
                  const float* __restrict__ c,      // (N, h, w, CLAT)
@@ -166,16 +169,19 @@ fpn_merge_kernel(const float* __restrict__ prev,   // (N, h/2, w/2, 32) or null
   const int hi = h / 2, wi = w / 2;
   const float sy = hi > 1 ? (float)(hi - 1) / (float)(h - 1) : 0.f;
   const float sx = wi > 1 ? (float)(wi - 1) / (float)(w - 1) : 0.f;
-  // one (row, image) per blockIdx.y/z: no 64-bit index arithmetic in the loop
-  const int y = blockIdx.y, n = blockIdx.z;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < w * 4; t += gridDim.x * blockDim.x) {
-    const int g = t & 3;
-    const int x = t >> 2;
-    const size_t pix = ((size_t)n * h + y) * w + x;
-    float v[8];
+  const int n = blockIdx.y;
+  const int g = threadIdx.x & 3;
+  const int hw = h * w;
+  // pixels of this thread: p0 + k*64 (a block covers 64*kMergeP consecutive pixels of image n)
+  const int p0 = blockIdx.x * (64 * kMergeP) + (threadIdx.x >> 2);
+  float v[kMergeP][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = 0.f;
-    if (prev) {
+  for (int k = 0; k < kMergeP; ++k) {
+    const int pix = p0 + k * 64;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[k][q] = s_latw[CLAT * kFpnC + g * 8 + q];
+    if (prev && pix < hw) {
+      const int y = pix / w, x = pix - y * w;
       const float* pn = prev + (size_t)n * hi * wi * kFpnC;
       const float fy = sy * (float)y, fx = sx * (float)x;
       const int ya = min((int)fy, hi - 1), xa = min((int)fx, wi - 1);
@@ -191,30 +197,45 @@ fpn_merge_kernel(const float* __restrict__ prev,   // (N, h/2, w/2, 32) or null
       for (int q = 0; q < 2; ++q) {
         const float4 a = ldg4(p00 + 4 * q), b = ldg4(p01 + 4 * q), cc = ldg4(p10 + 4 * q),
                      d = ldg4(p11 + 4 * q);
-        v[4 * q + 0] = a.x * w00 + b.x * w01 + cc.x * w10 + d.x * w11;
-        v[4 * q + 1] = a.y * w00 + b.y * w01 + cc.y * w10 + d.y * w11;
-        v[4 * q + 2] = a.z * w00 + b.z * w01 + cc.z * w10 + d.z * w11;
-        v[4 * q + 3] = a.w * w00 + b.w * w01 + cc.w * w10 + d.w * w11;
+        // same association as the fused level kernel: ((a*w00 + b*w01) + c*w10) + d*w11, then + bias
+        v[k][4 * q + 0] = (a.x * w00 + b.x * w01 + cc.x * w10 + d.x * w11) + v[k][4 * q + 0];
+        v[k][4 * q + 1] = (a.y * w00 + b.y * w01 + cc.y * w10 + d.y * w11) + v[k][4 * q + 1];
+        v[k][4 * q + 2] = (a.z * w00 + b.z * w01 + cc.z * w10 + d.z * w11) + v[k][4 * q + 2];
+        v[k][4 * q + 3] = (a.w * w00 + b.w * w01 + cc.w * w10 + d.w * w11) + v[k][4 * q + 3];
       }
     }
+  }
+  const float* cn = c + (size_t)n * hw * CLAT;
+  for (int ci = 0; ci < CLAT; ci += 4) {
+    float cs[kMergeP][4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] += s_latw[CLAT * kFpnC + g * 8 + k];
-    const float* cp = c + pix * CLAT;
-    for (int ci = 0; ci < CLAT; ci += 4) {
-      const float4 cv = ldg4(cp + ci);
-      const float cs[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float* wr = s_latw + (ci + j) * kFpnC + g * 8;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fmaf(cs[j], wr[k], v[k]);
-      }
+    for (int k = 0; k < kMergeP; ++k) {
+      const int pix = p0 + k * 64;
+      const float4 cv = pix < hw ? ldg4(cn + (size_t)pix * CLAT + ci) : make_float4(0.f, 0.f, 0.f, 0.f);
+      cs[k][0] = cv.x; cs[k][1] = cv.y; cs[k][2] = cv.z; cs[k][3] = cv.w;
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = round_tf32_if(v[k], round_out);
-    float* fo = feat + pix * kFpnC + g * 8;
-    st4(fo, make_float4(v[0], v[1], v[2], v[3]));
-    st4(fo + 4, make_float4(v[4], v[5], v[6], v[7]));
+    for (int j = 0; j < 4; ++j) {
+      const float4 wa = *reinterpret_cast<const float4*>(s_latw + (ci + j) * kFpnC + g * 8);
+      const float4 wb = *reinterpret_cast<const float4*>(s_latw + (ci + j) * kFpnC + g * 8 + 4);
+      const float wr[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int k = 0; k < kMergeP; ++k) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[k][q] = fmaf(cs[k][j], wr[q], v[k][q]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kMergeP; ++k) {
+    const int pix = p0 + k * 64;
+    if (pix < hw) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[k][q] = round_tf32_if(v[k][q], round_out);
+      float* fo = feat + ((size_t)n * hw + pix) * kFpnC + g * 8;
+      st4(fo, make_float4(v[k][0], v[k][1], v[k][2], v[k][3]));
+      st4(fo + 4, make_float4(v[k][4], v[k][5], v[k][6], v[k][7]));
+    }
   }
 }
 
@@ -266,6 +287,70 @@ conv2d_rgb8_kernel(const float* __restrict__ x, const float* __restrict__ w,
   float* yo = y + (((size_t)n * H + py) * W + px) * 8;
   st4(yo, make_float4(acc[0], acc[1], acc[2], acc[3]));
   st4(yo + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+}
+
+// Same, four consecutive output pixels per thread (W % 4 == 0): each input row segment
+// x-1 .. x+4 is loaded once (scalar, float4, scalar) and each tap's 8 weights are read from
+// shared memory once for the four pixels -- about a third of the instructions per pixel.
+__global__ void __launch_bounds__(256)
+conv2d_rgb8_x4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                      const float* __restrict__ bias, float slope, float* __restrict__ y, int N,
+                      int H, int W, int round_out) {
+  __shared__ __align__(16) float s_w[27 * 8 + 8];
+  for (int i = threadIdx.x; i < 27 * 8; i += blockDim.x) {
+    const int co = i & 7, r = i >> 3;            // r = ci*9 + ky*3 + kx  (torch (8,3,3,3) order)
+    s_w[i] = __ldg(w + (size_t)co * 27 + r);
+  }
+  if (threadIdx.x < 8) s_w[27 * 8 + threadIdx.x] = __ldg(bias + threadIdx.x);
+  __syncthreads();
+  const int px = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int py = blockIdx.y, n = blockIdx.z;
+  if (px >= W) return;
+  float acc[4][8];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[p][k] = s_w[27 * 8 + k];
+  const float* xn = x + (size_t)n * 3 * H * W;
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = py + ky - 1;
+      float in[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (iy >= 0 && iy < H) {
+        const float* row = xn + ((size_t)ci * H + iy) * W + px;
+        const float4 mid = ldg4(row);
+        in[1] = mid.x; in[2] = mid.y; in[3] = mid.z; in[4] = mid.w;
+        if (px > 0) in[0] = __ldg(row - 1);
+        if (px + 4 < W) in[5] = __ldg(row + 4);
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ci * 9 + ky * 3 + kx) * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ci * 9 + ky * 3 + kx) * 8 + 4);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float v = in[p + kx];
+          acc[p][0] = fmaf(v, w0.x, acc[p][0]); acc[p][1] = fmaf(v, w0.y, acc[p][1]);
+          acc[p][2] = fmaf(v, w0.z, acc[p][2]); acc[p][3] = fmaf(v, w0.w, acc[p][3]);
+          acc[p][4] = fmaf(v, w1.x, acc[p][4]); acc[p][5] = fmaf(v, w1.y, acc[p][5]);
+          acc[p][6] = fmaf(v, w1.z, acc[p][6]); acc[p][7] = fmaf(v, w1.w, acc[p][7]);
+        }
+      }
+    }
+  }
+  float* yo = y + (((size_t)n * H + py) * W + px) * 8;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float t = acc[p][k] >= 0.f ? acc[p][k] : acc[p][k] * slope;
+      acc[p][k] = round_tf32_if(t, round_out);
+    }
+    st4(yo + p * 8, make_float4(acc[p][0], acc[p][1], acc[p][2], acc[p][3]));
+    st4(yo + p * 8 + 4, make_float4(acc[p][4], acc[p][5], acc[p][6], acc[p][7]));
+  }
 }
 
 // x[..., c] = lrelu(x[..., c] + bias[c]) in place on a channels-last tensor (C % 4 == 0):
@@ -340,9 +425,9 @@ extern "C" int casmvs_fpn_merge_fwd(const float* prev, const float* c, const flo
                  "fpn_merge: h,w must be even when a coarser level is upsampled");
   CASMVS_REQUIRE(CLAT % 4 == 0 && CLAT > 0 && CLAT <= 64, "fpn_merge: CLAT must be a multiple of 4");
   if (N == 0) return 0;
-  CASMVS_REQUIRE(N <= 65535 && h <= 65535, "fpn_merge: N, h must be <= 65535");
+  CASMVS_REQUIRE(N <= 65535 && (long)h * w < (1l << 30), "fpn_merge: volume too large");
   const size_t smem = (size_t)(CLAT * kFpnC + kFpnC) * 4;
-  dim3 blocks((w * 4 + 255) / 256, h, N);
+  dim3 blocks((h * w + 64 * kMergeP - 1) / (64 * kMergeP), N);
   fpn_merge_kernel<<<blocks, 256, smem, as_stream(stream)>>>(prev, c, lat_w, lat_b, feat, N, h, w,
                                                             CLAT, round_tf32 ? 1 : 0);
   return after_launch("fpn_merge");
@@ -354,6 +439,13 @@ extern "C" int casmvs_conv2d_rgb8_fwd(const float* x, const float* w, const floa
   CASMVS_REQUIRE(x && w && bias && y, "conv2d_rgb8: null pointer");
   CASMVS_REQUIRE(N >= 0 && N <= 65535 && H >= 1 && H <= 65535 && W >= 1, "conv2d_rgb8: bad dims");
   if (N == 0) return 0;
+  if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int bx = W / 4 >= 256 ? 256 : ((W / 4 + 31) / 32) * 32;     // one block per row up to 1024 px
+    dim3 grd((W / 4 + bx - 1) / bx, H, N);
+    conv2d_rgb8_x4_kernel<<<grd, bx, 0, as_stream(stream)>>>(x, w, bias, slope, y, N, H, W,
+                                                             round_tf32 ? 1 : 0);
+    return after_launch("conv2d_rgb8");
+  }
   dim3 grd((W + 127) / 128, H, N);
   conv2d_rgb8_kernel<<<grd, 128, 0, as_stream(stream)>>>(x, w, bias, slope, y, N, H, W,
                                                          round_tf32 ? 1 : 0);

@@ -7,6 +7,8 @@
 //   get_depth_values                models/modules.py:34-49
 //   x2 bilinear upsample            models/mvsnet.py:231-234
 //   initial uniform planes          models/mvsnet.py:213-229
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace casmvs {
@@ -29,7 +31,12 @@ struct Cascade16 {
   __device__ __forceinline__ float result() const { return __fadd_rn(a0, a1); }
 };
 
-template <bool IS_PROB>
+// DT > 0: D is the compile-time constant DT (the cascade's 8 / 32 / 48): the D logits of a
+// pixel are loaded ONCE into registers (D independent loads in flight instead of three
+// dependent passes over global memory) and exp(l - m) is evaluated once per hypothesis.  The
+// arithmetic -- every operation and its order -- is the generic path's, so results are
+// bit-identical (tests/test_gpu_kernels.py::test_regress_register_path_bit_identical).
+template <bool IS_PROB, int DT>
 __global__ void __launch_bounds__(kK3Threads)
 regress_kernel(const float* __restrict__ logits, const float* __restrict__ dv, int dv_is_vector,
                float* __restrict__ depth, float* __restrict__ conf,
@@ -42,19 +49,44 @@ regress_kernel(const float* __restrict__ logits, const float* __restrict__ dv, i
   const size_t dstride = dv_is_vector ? 1 : (size_t)hw;
 
   float m = 0.f, denom = 1.f;
-  if (!IS_PROB) {
-    m = -INFINITY;
-    for (int d = 0; d < D; ++d) m = fmaxf(m, __ldg(lp + (size_t)d * hw));
-    denom = 0.f;
-    for (int d = 0; d < D; ++d) denom = __fadd_rn(denom, expf(__ldg(lp + (size_t)d * hw) - m));
-  }
   Cascade16 acc_depth, acc_idx;
-  for (int d = 0; d < D; ++d) {
-    float p = __ldg(lp + (size_t)d * hw);
-    if (!IS_PROB) p = __fdiv_rn(expf(p - m), denom);
-    if (prob) prob[(size_t)b * D * hw + (size_t)d * hw + pix] = p;
-    acc_depth.add(__fmul_rn(p, __ldg(dp + d * dstride)));
-    acc_idx.add(__fmul_rn(p, (float)d));
+  if constexpr (DT > 0) {
+    float l[DT];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) l[d] = __ldg(lp + (size_t)d * hw);
+    if (!IS_PROB) {
+      m = -INFINITY;
+#pragma unroll
+      for (int d = 0; d < DT; ++d) m = fmaxf(m, l[d]);
+      denom = 0.f;
+#pragma unroll
+      for (int d = 0; d < DT; ++d) {
+        l[d] = expf(l[d] - m);
+        denom = __fadd_rn(denom, l[d]);
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+      float p = l[d];
+      if (!IS_PROB) p = __fdiv_rn(p, denom);
+      if (prob) prob[(size_t)b * D * hw + (size_t)d * hw + pix] = p;
+      acc_depth.add(__fmul_rn(p, __ldg(dp + d * dstride)));
+      acc_idx.add(__fmul_rn(p, (float)d));
+    }
+  } else {
+    if (!IS_PROB) {
+      m = -INFINITY;
+      for (int d = 0; d < D; ++d) m = fmaxf(m, __ldg(lp + (size_t)d * hw));
+      denom = 0.f;
+      for (int d = 0; d < D; ++d) denom = __fadd_rn(denom, expf(__ldg(lp + (size_t)d * hw) - m));
+    }
+    for (int d = 0; d < D; ++d) {
+      float p = __ldg(lp + (size_t)d * hw);
+      if (!IS_PROB) p = __fdiv_rn(expf(p - m), denom);
+      if (prob) prob[(size_t)b * D * hw + (size_t)d * hw + pix] = p;
+      acc_depth.add(__fmul_rn(p, __ldg(dp + d * dstride)));
+      acc_idx.add(__fmul_rn(p, (float)d));
+    }
   }
   const float dep = acc_depth.result();
   const float fidx = acc_idx.result();
@@ -144,14 +176,29 @@ extern "C" int casmvs_regress_fwd(const float* logits, const float* depth_values
   CASMVS_REQUIRE(B >= 0 && B <= 65535 && D > 0 && h > 0 && w > 0, "regress: bad dims");
   if (B == 0) return 0;
   const int hw = h * w;
-  dim3 grd((hw + kK3Threads - 1) / kK3Threads, B);
   cudaStream_t st = as_stream(stream);
-  if (input_is_prob)
-    regress_kernel<true><<<grd, kK3Threads, 0, st>>>(logits, depth_values, dv_is_vector, depth,
-                                                     confidence, (long long*)index, prob, D, hw);
-  else
-    regress_kernel<false><<<grd, kK3Threads, 0, st>>>(logits, depth_values, dv_is_vector, depth,
-                                                      confidence, (long long*)index, prob, D, hw);
+  static int reg_path = -1;
+  if (reg_path < 0) {
+    const char* e = getenv("CASMVS_K3_REG");
+    reg_path = e ? atoi(e) : 1;
+  }
+  // small maps: narrower blocks so that every SM gets work
+  const int threads = (long)hw * B < (long)num_sms() * 4 * kK3Threads ? 32 : kK3Threads;
+  dim3 grd((hw + threads - 1) / threads, B);
+#define K3_LAUNCH(PROB, DT)                                                                   \
+  regress_kernel<PROB, DT><<<grd, threads, 0, st>>>(logits, depth_values, dv_is_vector, depth, \
+                                                    confidence, (long long*)index, prob, D, hw)
+#define K3_CASE(DT)                                    \
+  if (reg_path && D == DT) {                           \
+    if (input_is_prob) K3_LAUNCH(true, DT);            \
+    else K3_LAUNCH(false, DT);                         \
+    return after_launch("regress");                    \
+  }
+  K3_CASE(8) K3_CASE(32) K3_CASE(48)
+  if (input_is_prob) K3_LAUNCH(true, 0);
+  else K3_LAUNCH(false, 0);
+#undef K3_CASE
+#undef K3_LAUNCH
   return after_launch("regress");
 }
 

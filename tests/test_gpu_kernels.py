@@ -9,10 +9,13 @@ and a warped value by that times the local feature gradient.  Tolerances below
 are expressed on that basis and the fp64 test shows the kernel is at least as
 close to exact arithmetic as the reference is.
 """
+import os
+
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 from casmvsnet_pl_b200 import _lib, ops, synth           # noqa: E402
 from oracle import casmvs_oracle as O                    # noqa: E402
@@ -237,6 +240,35 @@ def test_regress_index_exact_given_identical_prob(golden, D):
     assert (conf.cpu() - g["confidence"]).abs().max() < 2.4e-7
 
 
+def test_regress_register_path_bit_identical(tmp_path):
+    """The D = 8/32/48 register-resident K3 path performs the generic path's operations in the
+    generic path's order: a child process with CASMVS_K3_REG=0 must reproduce it bit for bit."""
+    import subprocess, sys
+    code = (
+        "import sys, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from casmvsnet_pl_b200 import ops\n"
+        "out = {}\n"
+        "for D in (8, 32, 48):\n"
+        "    g = torch.Generator().manual_seed(D)\n"
+        "    lg = (torch.randn(2, D, 37, 53, generator=g) * 3).cuda()\n"
+        "    dv = (torch.rand(2, D, 37, 53, generator=g) * 500 + 400).cuda()\n"
+        "    d, c, i, p = ops.regress(lg, dv, want_index=True, want_prob=True)\n"
+        "    out[D] = [t.cpu() for t in (d, c, i, p)]\n"
+        "torch.save(out, sys.argv[1])\n" % ROOT)
+    import os
+    paths = []
+    for reg in ("1", "0"):
+        path = str(tmp_path / f"k3_{reg}.pt")
+        env = dict(os.environ, CASMVS_K3_REG=reg)
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=300)
+        paths.append(path)
+    a, b = torch.load(paths[0]), torch.load(paths[1])
+    for D in (8, 32, 48):
+        for ta, tb in zip(a[D], b[D]):
+            assert torch.equal(ta, tb)
+
+
 def test_depth_regression_api_vector_depths(golden):
     from casmvsnet_pl_b200.models.modules import depth_regression
     g = golden("regress_d32")
@@ -324,11 +356,13 @@ def test_fpn_merge_vs_torch_cpu(clat, hw, with_prev):
     assert torch.equal(got_r.view(torch.int32) & 0x1FFF, torch.zeros_like(got_r, dtype=torch.int32))
 
 
-def test_conv2d_rgb8_vs_torch_cpu():
-    """First FeatureNet block (ConvBnReLU(3,8,3,1,1) with folded ABN) from planar images."""
+@pytest.mark.parametrize("hw", [(37, 141), (21, 144), (9, 1280)])
+def test_conv2d_rgb8_vs_torch_cpu(hw):
+    """First FeatureNet block (ConvBnReLU(3,8,3,1,1) with folded ABN) from planar images
+    (one-pixel-per-thread kernel for ragged widths, four-pixel kernel for W % 4 == 0)."""
     import torch.nn.functional as F
     g = torch.Generator().manual_seed(3)
-    x = torch.randn(3, 3, 37, 141, generator=g)
+    x = torch.randn(3, 3, *hw, generator=g)
     w = torch.randn(8, 3, 3, 3, generator=g) * 0.3
     b = torch.randn(8, generator=g) * 0.1
     want = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.01)
