@@ -13,7 +13,13 @@
 //   * persistent CTAs, 6 warps (0-3 epilogue, 4 TMA producer, 5 MMA issuer); accumulators are
 //     re-zeroed by the epilogue after reading and handed back through tempty barriers.
 //
+//   * MODE_P5: the 5x5 stride-2 Conv2d layers of FeatureNet (conv1.0, conv2.0) as a planar
+//     convolution over the (views, H, W) volume: the same even/odd planes (10 columns, 35 rows:
+//     iw = 2*ow0-2+2j for kw = 0,2,4 at j, j+1, j+2; iw = 2*ow0-1+2j for kw = 1,3), 25 taps of
+//     K = Cin, N = Cout, one accumulator group per image.
+//
 // Replaces (reference, relative to /root/reference):
+//   ConvBnReLU(k=5, stride=2, pad=2)               models/modules.py:8-18, mvsnet.py:16,20
 //   ConvBnReLU3D(stride=2)                         models/modules.py:21-31, mvsnet.py:65,68,71
 //   ConvTranspose3d(k3,s2,p1,op1) + norm_act + skip models/mvsnet.py:74-87,99-101
 #include <stdlib.h>
@@ -29,7 +35,7 @@ using namespace casmvs::tc;
 using casmvs::tma::mbar_expect_tx;
 using casmvs::tma::tma_load_5d;
 
-enum { MODE_S2 = 0, MODE_T = 1 };
+enum { MODE_S2 = 0, MODE_T = 1, MODE_P5 = 2 };
 constexpr int kThreads2 = 6 * 32;
 constexpr int kProdWarp = 4, kIssueWarp = 5;
 
@@ -52,16 +58,16 @@ struct Cfg {
   static constexpr int CB = CIN > 32 ? 32 : CIN;            // channels per brick plane
   static constexpr int NB = CIN / CB;
   static constexpr int ROWB = CB * 4;                       // bytes per voxel = swizzle span
-  static constexpr int BR = MODE == MODE_S2 ? 33 : 17;      // brick rows
-  static constexpr int BW = 9;                              // brick columns per plane
-  static constexpr int NPL = (MODE == MODE_S2 ? 2 : 1) * NB;   // planes (= TMA loads) per slice
+  static constexpr int BR = MODE == MODE_S2 ? 33 : MODE == MODE_T ? 17 : 35;   // brick rows
+  static constexpr int BW = MODE == MODE_P5 ? 10 : 9;       // brick columns per plane
+  static constexpr int NPL = (MODE == MODE_T ? 1 : 2) * NB; // planes (= TMA loads) per slice
   static constexpr int kPlaneData = BR * BW * ROWB;
   static constexpr int kPlaneBytes = (kPlaneData + 1023) / 1024 * 1024;
   static constexpr int kSlotBytes = NPL * kPlaneBytes;
   // accumulator group (columns per output group) and B image rows per tap
-  static constexpr int GW = MODE == MODE_S2 ? (COUT <= 16 ? 16 : 32) : 8 * COUT;
-  static constexpr int BROWS = MODE == MODE_S2 ? 3 * GW : 12 * COUT;
-  static constexpr int NTAP = MODE == MODE_S2 ? 9 : 4;      // A views per input slice
+  static constexpr int GW = MODE == MODE_T ? 8 * COUT : (COUT <= 16 ? 16 : 32);
+  static constexpr int BROWS = MODE == MODE_S2 ? 3 * GW : MODE == MODE_T ? 12 * COUT : GW;
+  static constexpr int NTAP = MODE == MODE_S2 ? 9 : MODE == MODE_T ? 4 : 25;   // A views per slice
   static constexpr int kWBytes = NTAP * CIN * BROWS * 4;
   static constexpr int kFixed = kWBytes + 2 * 32 * 4 + 192 + 32 * 8 + 32 * 8 + 1024;
   static constexpr int SLOTS = (kFixed + 4 * kSlotBytes <= 227 * 1024) ? 4
@@ -98,7 +104,7 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = tmem_cols_for2(p.dchunk * GW);
   const int total_items = p.B * p.nchunks * p.tiles_h * p.tiles_w;
-  const int Dm = MODE == MODE_S2 ? p.Do : p.Di;              // M-space depth
+  const int Dm = MODE == MODE_T ? p.Di : p.Do;               // M-space depth
 
   // ---- one-time setup ----
   {
@@ -143,7 +149,8 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
     const int g0 = ck * p.dchunk, g1 = min(Dm, g0 + p.dchunk);
     const int ng = g1 - g0;                                  // accumulator groups of this item
     // input slices walked: S2: s = 2*g0-1 .. 2*g1-1  (2*ng+1);  T: s = g0 .. g1  (ng+1)
-    const int nslices = MODE == MODE_S2 ? 2 * ng + 1 : ng + 1;
+    // P5: s = g0 .. g1-1 (every image is its own group)
+    const int nslices = MODE == MODE_S2 ? 2 * ng + 1 : MODE == MODE_T ? ng + 1 : ng;
     const int s_first = MODE == MODE_S2 ? 2 * g0 - 1 : g0;
 
     if (warp == kProdWarp) {
@@ -157,9 +164,10 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
           mbar_expect_tx(bar_full + 8 * slot, C::NPL * C::kPlaneData);
 #pragma unroll
           for (int pl = 0; pl < C::NPL; ++pl) {
-            const int nb = MODE == MODE_S2 ? pl >> 1 : pl;
-            const int wc = MODE == MODE_S2 ? 2 * w0 - 1 + (pl & 1) : w0;
-            const int hc = MODE == MODE_S2 ? 2 * h0 - 1 : h0;
+            const int nb = MODE == MODE_T ? pl : pl >> 1;
+            const int wc = MODE == MODE_S2 ? 2 * w0 - 1 + (pl & 1)
+                           : MODE == MODE_T ? w0 : 2 * w0 - 2 + (pl & 1);
+            const int hc = MODE == MODE_S2 ? 2 * h0 - 1 : MODE == MODE_T ? h0 : 2 * h0 - 2;
             tma_load_5d(dst + pl * C::kPlaneBytes, &xmap, bar_full + 8 * slot, nb * C::CB, wc,
                         hc, s_first + it, b);
           }
@@ -169,7 +177,7 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
     } else if (warp == kIssueWarp) {
       // ===================== MMA issuer (warp-uniform, elect-predicated) =====================
       constexpr uint32_t a_lbo = 16;
-      constexpr uint32_t a_sbo = (MODE == MODE_S2 ? 2 : 1) * BW * C::ROWB;
+      constexpr uint32_t a_sbo = (MODE == MODE_T ? 1 : 2) * BW * C::ROWB;
       constexpr uint32_t b_lbo = BROWS * 16, b_sbo = 128;
       constexpr int KPB = C::CB / 8;                          // K=8 steps per plane
       const uint32_t elected = elect_one();
@@ -194,6 +202,8 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
             if (a >= 1) done = a - 1;
             last = hi;
           }
+        } else if (MODE == MODE_P5) {
+          col = it * GW; row0 = 0; ncols = GW; done = it; last = it;
         } else {
           // T: slice it -> group it (blocks kd=1,kd=2; if it < ng) and group it-1 (block kd=0)
           const bool cur = it < ng, prev = it >= 1;
@@ -219,6 +229,10 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
             const int kh = tap / 3, kw = tap % 3;
             a_tap = (kh * BW + (kw == 2 ? 1 : 0)) * C::ROWB;
             pl0 = kw == 1 ? 1 : 0; plstep = 2;
+          } else if (MODE == MODE_P5) {
+            const int kh = tap / 5, kw = tap % 5;
+            a_tap = (kh * BW + (kw >> 1)) * C::ROWB;
+            pl0 = kw & 1; plstep = 2;
           } else {
             const int sh = tap >> 1, sw = tap & 1;
             a_tap = (sh * BW + sw) * C::ROWB;
@@ -255,7 +269,7 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
           continue;
         }
         tc_fence_after();
-        if constexpr (MODE == MODE_S2) {
+        if constexpr (MODE != MODE_T) {
           float acc[GW];
           tmem_ld<GW>(lane_base + g * GW, acc);
 #pragma unroll
@@ -386,6 +400,22 @@ __global__ void build_image_tma2_kernel(const float* __restrict__ wpk, float* __
   }
 }
 
+// MODE_P5 image [tap = kh*5+kw][cq][co (GW rows)][4] from the torch Conv2d weight (Cout,Cin,5,5)
+template <int CIN, int COUT>
+__global__ void build_image_p5_kernel(const float* __restrict__ wt, float* __restrict__ img) {
+  using C = Cfg<MODE_P5, CIN, COUT>;
+  constexpr int CQ = C::CQ, GW = C::GW;
+  constexpr int total = 25 * CIN * GW;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int jq = t & 3;
+    const int co = (t >> 2) % GW;
+    const int r = (t >> 2) / GW;             // tap*CQ + cq
+    const int cq = r % CQ, tap = r / CQ;
+    const int ci = cq * 4 + jq;
+    img[t] = co < COUT ? to_tf32(__ldg(wt + ((size_t)co * CIN + ci) * 25 + tap)) : 0.f;
+  }
+}
+
 template <int MODE, int CIN, int COUT>
 static int launch2(const float* x, const float* wpk, Params p, cudaStream_t st) {
   using C = Cfg<MODE, CIN, COUT>;
@@ -403,9 +433,11 @@ static int launch2(const float* x, const float* wpk, Params p, cudaStream_t st) 
     attr_set = true;
   }
   // S2: box {CB, 17 traversed -> 9 loaded, 33, 1, 1} walking W with stride 2; T: {CB, 9, 17}
+  // P5: box {CB, 19 traversed -> 10 loaded, 35, 1, 1} walking W with stride 2
   const CUtensorMap* map =
-      MODE == MODE_S2 ? tma::input_map(x, p.B, p.Di, p.Hi, p.Wi, CIN, C::CB, 17, C::BR, 2)
-                      : tma::input_map(x, p.B, p.Di, p.Hi, p.Wi, CIN, C::CB, C::BW, C::BR, 1);
+      MODE == MODE_S2   ? tma::input_map(x, p.B, p.Di, p.Hi, p.Wi, CIN, C::CB, 17, C::BR, 2)
+      : MODE == MODE_P5 ? tma::input_map(x, p.B, p.Di, p.Hi, p.Wi, CIN, C::CB, 19, C::BR, 2)
+                        : tma::input_map(x, p.B, p.Di, p.Hi, p.Wi, CIN, C::CB, C::BW, C::BR, 1);
   if (!map) return -2;
   static int per_sm_env = -1;
   if (per_sm_env < 0) {
@@ -416,8 +448,8 @@ static int launch2(const float* x, const float* wpk, Params p, cudaStream_t st) 
   int per_sm = smem_limit < 2 ? smem_limit : 2;
   if (per_sm_env > 0 && per_sm_env < smem_limit) per_sm = per_sm_env;
   if (per_sm < 1) per_sm = 1;
-  const int Dm = MODE == MODE_S2 ? p.Do : p.Di;
-  const int Hm = MODE == MODE_S2 ? p.Ho : p.Hi, Wm = MODE == MODE_S2 ? p.Wo : p.Wi;
+  const int Dm = MODE == MODE_T ? p.Di : p.Do;
+  const int Hm = MODE == MODE_T ? p.Hi : p.Ho, Wm = MODE == MODE_T ? p.Wi : p.Wo;
   p.tiles_w = (Wm + kTileW - 1) / kTileW;
   p.tiles_h = (Hm + kTileH - 1) / kTileH;
   const int nco = p.Cout / COUT;
@@ -438,7 +470,10 @@ static int launch2(const float* x, const float* wpk, Params p, cudaStream_t st) 
                                   (size_t)C::kWBytes * nco, &hit);
   if (!img) { set_error("conv3d_tma2: cannot allocate the weight image"); return -2; }
   if (!hit) {
-    build_image_tma2_kernel<MODE, CIN, COUT><<<64, 256, 0, st>>>(wpk, img, p.Cout);
+    if constexpr (MODE == MODE_P5)
+      build_image_p5_kernel<CIN, COUT><<<32, 256, 0, st>>>(wpk, img);
+    else
+      build_image_tma2_kernel<MODE, CIN, COUT><<<64, 256, 0, st>>>(wpk, img, p.Cout);
     if (int rc = after_launch("conv3d_tma2/build_image")) return rc;
   }
   p.bimg = img;
@@ -484,3 +519,24 @@ int conv3d_tma2(const float* x, const float* wpk, const float* scale, const floa
 }
 
 }  // namespace casmvs
+
+using namespace casmvs;
+
+extern "C" int casmvs_conv2d_5x5s2_fwd(const float* x, const float* w, const float* shift,
+                                       float slope, float* y, int N, int Cin, int Cout, int H,
+                                       int W, int round_tf32, void* stream) {
+  CASMVS_REQUIRE(x && w && y, "conv2d_5x5s2: null pointer");
+  CASMVS_REQUIRE(N >= 0 && H >= 2 && W >= 2, "conv2d_5x5s2: bad dims");
+  CASMVS_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "conv2d_5x5s2: x must be 16 B aligned");
+  if (N == 0) return 0;
+  tma2::Params p;
+  p.scale = nullptr; p.shift = shift; p.skip = nullptr; p.y = y; p.slope = slope;
+  p.B = 1; p.Di = N; p.Hi = H; p.Wi = W; p.Do = N; p.Ho = (H - 1) / 2 + 1; p.Wo = (W - 1) / 2 + 1;
+  p.Cout = Cout; p.round_out = round_tf32 ? 1 : 0;
+  cudaStream_t st = as_stream(stream);
+  if (Cin == 8 && Cout == 16) return tma2::launch2<tma2::MODE_P5, 8, 16>(x, w, p, st);
+  if (Cin == 16 && Cout == 32) return tma2::launch2<tma2::MODE_P5, 16, 32>(x, w, p, st);
+  set_error("conv2d_5x5s2: only the FeatureNet shapes 8->16 and 16->32 are built (got %d->%d)",
+            Cin, Cout);
+  return -1;
+}

@@ -42,9 +42,9 @@ class FeatureNet(nn.Module):
     # cuDNN would run fp32 convs as TF32 on B200 by default; the reference path is fp32
     # (opt.py:69-70), so IEEE fp32 is kept unless the model runs in its tf32 precision mode.
     allow_tf32 = False
-    # tf32 precision mode, inference: the 3x3 stride-1 convs run on tcgen05 as planar (1x3x3)
-    # convolutions over the (views, H, W) volume, the first block and the top-down merges in
-    # this library's own kernels; only the two 5x5 stride-2 convs stay with cuDNN
+    # tf32 precision mode, inference: the 3x3 stride-1 and 5x5 stride-2 convs run on tcgen05 as
+    # planar convolutions over the (views, H, W) volume, the first block and the top-down
+    # merges in this library's own kernels: no cuDNN kernel is left on this path
     tensor_path = True
     # the reference's inference script turns cuDNN autotuning on (eval.py:19); without it
     # cuDNN's heuristics pick FFT/sgemm algorithms that are several times slower here
@@ -86,6 +86,8 @@ class FeatureNet(nn.Module):
             for i in (1, 3, 4, 6, 7):               # the 3x3 stride-1 blocks
                 w = cache[i][0]
                 packed[i] = ops.pack_conv3d_weight(w.contiguous(), ops.CONV_PLANAR)
+            for i in (2, 5):                        # the 5x5 stride-2 blocks: plain (O,I,5,5)
+                packed[i] = ops.pack_conv2d_5x5s2_weight(cache[i][0])
             self._pack_cache, self._pack_key = packed, key
         skey = tuple((t.data_ptr(), t._version) for t in (self.smooth0.weight, self.smooth1.weight))
         if getattr(self, "_smooth_key", None) != skey:
@@ -103,11 +105,8 @@ class FeatureNet(nn.Module):
                                      keep_fp32=keep)
 
         def strided(t, i):
-            w, b, stride, pad, slope = cache[i]
-            t = F.conv2d(t, w, None, stride, pad)
-            if not t.is_contiguous(memory_format=torch.channels_last):
-                t = t.contiguous(memory_format=torch.channels_last)
-            return ops.bias_lrelu_(t, b, slope, round_tf32=True)
+            _, b, _, _, slope = cache[i]
+            return ops.conv2d_5x5s2(t, packed[i], b, slope, round_tf32=True)
 
         w0, b0, _, _, slope0 = cache[0]
         t = ops.conv2d_rgb8(x, w0, b0, slope0, round_tf32=True)

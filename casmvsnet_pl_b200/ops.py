@@ -346,6 +346,35 @@ def conv2d_rgb8(x, w, bias, slope, round_tf32=False):
     return y
 
 
+def pack_conv2d_5x5s2_weight(weight):
+    """Private copy of a (Cout,Cin,5,5) Conv2d weight for conv2d_5x5s2.  The library caches the
+    tensor-core operand image it builds from a weight buffer BY POINTER, so weights must come
+    through here (it drops the cache, like pack_conv3d_weight) and must not be edited in place."""
+    _require_cuda(weight)
+    assert weight.dim() == 4 and tuple(weight.shape[2:]) == (5, 5)
+    invalidate_weight_cache()
+    return weight.detach().clone(memory_format=torch.contiguous_format)
+
+
+def conv2d_5x5s2(x, w, shift, slope, round_tf32=False):
+    """5x5 stride-2 pad-2 Conv2d + shift + LeakyReLU on tcgen05 (FeatureNet conv1.0 / conv2.0
+    with folded ABN).  x (N,Cin,H,W) channels-last, w (Cout,Cin,5,5) from
+    pack_conv2d_5x5s2_weight -> (N,Cout,H/2,W/2)."""
+    _require_cuda(x, w, shift)
+    _no_grad_only(x)
+    xs = x.contiguous(memory_format=torch.channels_last)
+    N, cin, H, W = xs.shape
+    cout = w.shape[0]
+    assert tuple(w.shape) == (cout, cin, 5, 5) and w.is_contiguous()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((N, cout, Ho, Wo), device=x.device, dtype=torch.float32,
+                    memory_format=torch.channels_last)
+    check(_lib.load().casmvs_conv2d_5x5s2_fwd(_ptr(xs), _ptr(w), _ptr(shift), float(slope),
+                                              _ptr(y), N, cin, cout, H, W,
+                                              1 if round_tf32 else 0, _stream()), "conv2d_5x5s2")
+    return y
+
+
 def bias_lrelu_(x, bias, slope, round_tf32=False):
     """In-place LeakyReLU(x + bias[c]) on a channels-last (N,C,h,w) tensor (optionally stored
     TF32-rounded for a tensor-core consumer)."""

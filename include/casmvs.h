@@ -201,6 +201,16 @@ int casmvs_fpn_merge_fwd(const float* prev, const float* c, const float* lat_w,
 int casmvs_conv2d_rgb8_fwd(const float* x, const float* w, const float* bias, float slope,
                            float* y, int N, int H, int W, int round_tf32, void* stream);
 
+/* The 5x5 stride-2 blocks of FeatureNet (ConvBnReLU(8,16,5,2,2) / (16,32,5,2,2), mvsnet.py:16,20
+ * + modules.py:8-18) with the eval-mode ABN folded, on tcgen05 (TF32 operands):
+ *   y = LeakyReLU(conv5x5_s2_p2(x, w) + shift)
+ * x (N,H,W,Cin) channels-last, w (Cout,Cin,5,5) torch layout already multiplied by the ABN
+ * scale, y (N,(H-1)/2+1,(W-1)/2+1,Cout) channels-last, optionally stored TF32-rounded.  The
+ * operand image built from `w` is cached by pointer (casmvs_invalidate_weight_cache). */
+int casmvs_conv2d_5x5s2_fwd(const float* x, const float* w, const float* shift, float slope,
+                            float* y, int N, int Cin, int Cout, int H, int W, int round_tf32,
+                            void* stream);
+
 /* In-place x[...,c] = LeakyReLU(x[...,c] + bias[c]) on a channels-last tensor (C % 4 == 0):
  * the epilogue of a folded conv + eval-mode ABN block (models/modules.py:8-18). */
 int casmvs_bias_lrelu_nhwc(float* x, const float* bias, float slope, size_t numel, int C,

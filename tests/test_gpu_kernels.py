@@ -397,6 +397,23 @@ def test_planar_conv_tensor_core_vs_torch_cpu(cin, cout, hw):
     assert (rounded - got.cpu()).abs().max() <= 2.0 ** -11 * got.abs().max().item()
 
 
+@pytest.mark.parametrize("cin,cout,hw", [(8, 16, (64, 96)), (16, 32, (36, 50)), (8, 16, (18, 34))])
+def test_conv2d_5x5s2_tensor_core_vs_torch_cpu(cin, cout, hw):
+    """FeatureNet's 5x5 stride-2 blocks on tcgen05 (even/odd TMA planes, 25 taps) vs torch fp32."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    x = torch.randn(3, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, 5, 5, generator=g) * 0.05
+    b = torch.randn(cout, generator=g) * 0.1
+    want = F.leaky_relu(F.conv2d(x, w, b, stride=2, padding=2), 0.01)
+    wp = ops.pack_conv2d_5x5s2_weight(w.to(DEV))
+    got = ops.conv2d_5x5s2(x.to(DEV).contiguous(memory_format=torch.channels_last), wp,
+                           b.to(DEV), 0.01)
+    assert got.shape == want.shape and ops.is_channels_last_feats(got)
+    err = stats(f"5x5s2 {cin}->{cout}", got.cpu(), want)
+    assert err.max() < 1.5e-3 * want.abs().max().item()
+
+
 # ----------------------------------------------------------------------------- K2 on tcgen05
 @pytest.mark.parametrize("kind,cin,cout,dims", [
     ("conv1", 8, 8, (5, 20, 13)), ("conv1", 16, 8, (16, 40, 24)), ("conv1", 32, 8, (8, 32, 40)),
