@@ -99,7 +99,7 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
                  s_bar = s_base + C::kBarOff;
   float* s_param = reinterpret_cast<float*>(smem + C::kParamOff);
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 64, bar_tfull = s_bar + 192,
-                 bar_tempty = s_bar + 448;
+                 bar_tempty = s_bar + 448, bar_w = s_bar + 136;   // bar_w: weight image landed
   volatile uint32_t* s_tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + C::kBarOff + 128);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t tmem_cols = tmem_cols_for2(p.dchunk * GW);
@@ -113,11 +113,11 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
     else if (t < 2 * SLOTS) mbar_init(bar_empty + 8 * (t - SLOTS), 1);
     else if (t >= 32 && t < 64) mbar_init(bar_tfull + 8 * (t - 32), 1);
     else if (t >= 64 && t < 96) mbar_init(bar_tempty + 8 * (t - 64), 128);
-    if (t < 96) fence_barrier_init();
+    else if (t == 96) mbar_init(bar_w, 1);
+    if (t < 97) fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(smem_u32((const void*)s_tmem_ptr), tmem_cols);
   const int co_base = blockIdx.y * COUT;
-  load_image_async(s_w, p.bimg + (size_t)blockIdx.y * (C::kWBytes / 4), C::kWBytes);
   for (int i = threadIdx.x; i < 32; i += kThreads2) {
     s_param[i] = (i < COUT) ? (p.scale ? __ldg(p.scale + co_base + i) : 1.f) : 0.f;
     s_param[32 + i] = (i < COUT) ? (p.shift ? __ldg(p.shift + co_base + i) : 0.f) : 0.f;
@@ -127,6 +127,7 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_ptr;
+  if (threadIdx.x == 0) tma::load_image_bulk(s_w, p.bimg + (size_t)blockIdx.y * (C::kWBytes / 4), C::kWBytes, bar_w);
   if (warp < 4) {
     for (int c = 0; c < p.dchunk * GW; c += 16)
       tmem_zero16(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
@@ -136,6 +137,7 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   __syncthreads();
   tc_fence_after();
 
+  bool w_ready = false;                             // MMA issuer: weight image has landed
   uint32_t gs = 0;                                  // slices processed before this item
   int ep = 0;                                       // items processed by this CTA
   for (int item0 = blockIdx.x; item0 < total_items; item0 += gridDim.x, ++ep) {
@@ -216,6 +218,7 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
         const uint32_t idesc = make_idesc(128, ncols);
         const uint32_t acc = tmem_base + col;
         mbar_wait(bar_full + 8 * (g % SLOTS), (g / SLOTS) & 1);
+        if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
         if (ep > 0) {
           for (; waited <= last; ++waited) mbar_wait(bar_tempty + 8 * waited, (ep - 1) & 1);
         }

@@ -121,7 +121,7 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
                  s_bar = s_base + S::kBarOff;
   float* s_param = reinterpret_cast<float*>(smem + S::kParamOff);
   const uint32_t bar_full = s_bar, bar_empty = s_bar + 64, bar_tfull = s_bar + 192,
-                 bar_tempty = s_bar + 448;
+                 bar_tempty = s_bar + 448, bar_w = s_bar + 136;   // bar_w: weight image landed
   volatile uint32_t* s_tmem_ptr = reinterpret_cast<volatile uint32_t*>(smem + S::kBarOff + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,10 +138,10 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
     else if (t < 2 * SLOTS) mbar_init(bar_empty + 8 * (t - SLOTS), 1);
     else if (t >= 32 && t < 64) mbar_init(bar_tfull + 8 * (t - 32), 1);
     else if (t >= 64 && t < 96) mbar_init(bar_tempty + 8 * (t - 64), 128);
-    if (t < 96) fence_barrier_init();
+    else if (t == 96) mbar_init(bar_w, 1);
+    if (t < 97) fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(smem_u32((const void*)s_tmem_ptr), tmem_cols);
-  load_image_async(s_w, p.bimg, S::kWBytes);
   for (int i = threadIdx.x; i < 8; i += kThreads8) {
     s_param[i] = (i < p.Cout) ? (p.scale ? __ldg(p.scale + i) : 1.f) : 0.f;
     s_param[8 + i] = (i < p.Cout) ? (p.shift ? __ldg(p.shift + i) : 0.f) : 0.f;
@@ -151,6 +151,7 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem_ptr;
+  if (threadIdx.x == 0) tma::load_image_bulk(s_w, p.bimg, S::kWBytes, bar_w);
   if (warp < 4) {
     for (int c = 0; c < p.dchunk * kG + 8; c += 8)
       tmem_zero8(tmem_base + ((uint32_t)(warp * 32) << 16) + c);
@@ -161,6 +162,7 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   tc_fence_after();
 
   if (threadIdx.x == 0) N8_STAMP(3, 0, 1);
+  bool w_ready = false;                             // MMA issuer: weight image has landed
   uint32_t gs = 0;                                  // slices processed before this item (all roles)
   int ep = 0;                                       // items processed by this CTA
   for (int item0 = blockIdx.x; item0 < total_items; item0 += gridDim.x, ++ep) {
@@ -213,6 +215,7 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
         const uint32_t acc = tmem_base + j_lo * kG;
         if (lane == 0) N8_STAMP(1, g, 0);
         mbar_wait(bar_full + 8 * (g % SLOTS), (g / SLOTS) & 1);
+        if (!w_ready) { mbar_wait(bar_w, 0); w_ready = true; }
         if (lane == 0) N8_STAMP(1, g, 1);
         // Every group this slice touches -- including the pad columns on group it+1 -- must
         // have been drained and re-zeroed by the epilogue of the previous item.

@@ -21,6 +21,22 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// Weight image -> shared memory as 1-D bulk copies issued by ONE thread and completed on an
+// mbarrier (armed here with the byte count): the CTA's other warps go straight to their roles
+// and only the MMA issuer waits for it, so the (14-110 KB) image fetch overlaps the first
+// input-brick loads instead of preceding them.  bytes % 16 == 0, both sides 16 B aligned.
+__device__ __forceinline__ void load_image_bulk(uint32_t dst_smem, const float* src, int bytes,
+                                                uint32_t bar) {
+  mbar_expect_tx(bar, (uint32_t)bytes);
+  for (int off = 0; off < bytes; off += 32768) {
+    const uint32_t n = (uint32_t)(bytes - off < 32768 ? bytes - off : 32768);
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst_smem + off), "l"(reinterpret_cast<const char*>(src) + off), "r"(n), "r"(bar)
+        : "memory");
+  }
+}
+
 // Tiled tensor map over the activation tensor x (B,D,H,W,C) viewed as {C, W, H, D, B} with box
 // {CB, box_w, box_h, 1, 1}, swizzle = CB*4 bytes (128/64/32), out-of-bounds elements zero-filled
 // (= the convolution's zero padding).  stride_w = 2: the box walks every second voxel along W
