@@ -407,11 +407,15 @@ def main():
             "metric": METRIC, "value": value, "unit": "depth-maps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else f"f32 (3D-conv products {args.precision})",
+            "dtype": "f32" if args.precision == "fp32" else f"f32 (conv products {args.precision}, fp32 accumulate)",
             "data": "synthetic",
             "config": {"workload": "cfg2: 640x512, V=3, D=48/32/8, variance cost, B=1 per GPU "
                                    "(BASELINE.json configs[1])",
-                       "step": "CascadeMVSNet.forward = FeatureNet (cuDNN fp32) + 3 cascade stages",
+                       "step": ("CascadeMVSNet.forward = FeatureNet (cuDNN fp32 convs + fused FPN "
+                                "kernel) + 3 cascade stages") if args.precision == "fp32" else
+                               ("CascadeMVSNet.forward = FeatureNet (own kernels: planar tcgen05 "
+                                "convs, RGB block, FPN merges) + 3 cascade stages (K4, K1, K2 x 11 "
+                                "layers on tcgen05, K3)"),
                        "parallelism": f"dp{world} (independent reference views per rank, one "
                                       "all_gather of depth_0 per step)" if world > 1 else "single GPU",
                        "precision": args.precision,

@@ -265,7 +265,30 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
       const int m = warp * 32 + lane;
       const int mh = h0 + (m >> 3), mw = w0 + (m & 7);          // M-space voxel of this thread
       const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+      // MODE_T: the skip tensor (output-shaped, 8 parity classes per input voxel) is prefetched
+      // in batches of 64 floats per thread BEFORE the accumulator is waited for, so its HBM
+      // latency overlaps the MMAs instead of sitting in the epilogue's serial chain
+      constexpr int CPB = COUT == 8 ? 8 : 4;                    // classes per skip batch
+      constexpr int C4 = COUT / 4;
+      float4 sk[MODE == MODE_T ? CPB * C4 : 1];
+      auto load_skip = [&](int g, int cls0) {
+        if constexpr (MODE == MODE_T) {
+#pragma unroll
+          for (int q = 0; q < CPB; ++q) {
+            const int cc = cls0 + q;
+            const int pd = cc >> 2, ph = (cc >> 1) & 1, pw = cc & 1;
+            const int od = 2 * (g0 + g) + pd, oh = 2 * mh + ph, ow = 2 * mw + pw;
+            const size_t o =
+                ((((size_t)b * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.Cout + co_base;
+#pragma unroll
+            for (int c = 0; c < C4; ++c)
+              sk[q * C4 + c] = (mh < p.Hi && mw < p.Wi) ? ldg4(p.skip + o + 4 * c)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      };
       for (int g = 0; g < p.dchunk; ++g) {
+        if (MODE == MODE_T && p.skip && g < ng) load_skip(g, 0);
         mbar_wait(bar_tfull + 8 * g, ep & 1);
         if (g >= ng) {                                          // unused group: handshake only
           mbar_arrive(bar_tempty + 8 * g);
@@ -315,6 +338,7 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
               tc_fence_before();
               mbar_arrive(bar_tempty + 8 * g);
             }
+            if (COUT != 8 && cls == CPB && p.skip) load_skip(g, CPB);   // second skip batch
             constexpr int NC = COUT == 8 ? 2 : 1;               // classes held in acc[]
 #pragma unroll
             for (int q = 0; q < NC; ++q) {
@@ -333,7 +357,7 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
                     v[k] = t >= 0.f ? t : t * p.slope;
                   }
                   if (p.skip) {
-                    const float4 s4 = ldg4(p.skip + o + c);
+                    const float4 s4 = sk[(cc % CPB) * C4 + c / 4];
                     v[0] += s4.x; v[1] += s4.y; v[2] += s4.z; v[3] += s4.w;
                   }
                   if (p.round_out) {

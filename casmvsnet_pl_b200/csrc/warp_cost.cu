@@ -384,8 +384,8 @@ __device__ __forceinline__ void stg_tex(float* p, const u64 (&v)[CPT / 2]) {
   }
 }
 
-template <int NSRC, int CT, int CPT, bool SKIP>
-__global__ void __launch_bounds__(kK1Threads, CPT == 4 ? 6 : 4)
+template <int NSRC, int CT, int CPT, bool SKIP, int MINB>
+__global__ void __launch_bounds__(kK1Threads, MINB)
 warp_var_kernel(const float* __restrict__ feats, const float* __restrict__ proj,
                 const float* __restrict__ dv, float* __restrict__ cost, int D, int h, int w,
                 int dchunk, int round_tf32) {
@@ -506,9 +506,20 @@ static bool launch_var(cudaStream_t st, const float* f, const float* p, const fl
   const long threads = (long)h * w * (CT / cpt);
   dim3 grd((unsigned)((threads + kK1Threads - 1) / kK1Threads), (unsigned)B,
            (unsigned)((D + dchunk - 1) / dchunk));
-#define LV(CPT_, SKIP_) warp_var_kernel<NSRC, CT, CPT_, SKIP_><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, D, h, w, dchunk, rnd)
-  if (cpt == 4) { if (skip) LV(4, true); else LV(4, false); }
-  else { if (skip) LV(8, true); else LV(8, false); }
+  // resident blocks per SM the register allocation is asked to allow (CASMVS_K1_MINB, 4..6):
+  // 4 -> 128 registers (all eight taps of both views in flight), 5 -> 96, 6 -> 80, 8 -> 64
+  static int minb = -1;
+  if (minb < 0) {
+    const char* e = getenv("CASMVS_K1_MINB");
+    minb = e ? atoi(e) : 6;     // measured (bench_k1.py): 4 -> 0.186 ms, 5 -> 0.182, 6 -> 0.174
+  }
+#define LV(CPT_, SKIP_, MB_) warp_var_kernel<NSRC, CT, CPT_, SKIP_, MB_><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, D, h, w, dchunk, rnd)
+  if (cpt == 4) { if (skip) LV(4, true, 6); else LV(4, false, 6); }
+  else if (skip) LV(8, true, 4);
+  else if (minb == 5) LV(8, false, 5);
+  else if (minb == 6) LV(8, false, 6);
+  else if (minb == 8) LV(8, false, 8);
+  else LV(8, false, 4);
 #undef LV
   return true;
 }
