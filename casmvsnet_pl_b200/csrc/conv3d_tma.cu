@@ -391,10 +391,8 @@ static int launch(const float* x, const float* wpk, Params p, cudaStream_t st) {
   const int nco = p.cout_total / p.Cout;
   int cap = pow2_floor(512 / per_sm) / GW;
   if (cap > 32) cap = 32;
-  int dchunk = p.D < cap ? p.D : cap;
   const long cols = (long)p.B * p.tiles_w * p.tiles_h;
-  while (dchunk > 4 && cols * nco * ((p.D + dchunk - 1) / dchunk) < (long)num_sms() * per_sm)
-    dchunk = (dchunk + 1) / 2;
+  int dchunk = pick_dchunk(p.D, cap, cols, (long)num_sms() * per_sm / nco, 1, p.planar ? 0 : 2);
   if (dchunk_env > 0 && dchunk_env <= cap) dchunk = dchunk_env < p.D ? dchunk_env : p.D;
   p.dchunk = dchunk;
   p.nchunks = (p.D + dchunk - 1) / dchunk;

@@ -483,12 +483,10 @@ static int launch2(const float* x, const float* wpk, Params p, cudaStream_t st) 
   int cap = tma::pow2_floor(512 / per_sm) / C::GW;
   if (cap < 1) { per_sm = 1; cap = 512 / C::GW; }
   if (cap > 32) cap = 32;
-  // equal chunks
-  int nchunks = (Dm + cap - 1) / cap;
-  int dchunk = (Dm + nchunks - 1) / nchunks;
   const long cols = (long)p.B * p.tiles_w * p.tiles_h;
-  while (dchunk > 2 && cols * nco * ((Dm + dchunk - 1) / dchunk) < (long)num_sms() * per_sm)
-    dchunk = (dchunk + 1) / 2;
+  const int dchunk = tma::pick_dchunk(Dm, cap, cols, (long)num_sms() * per_sm / nco,
+                                      MODE == MODE_S2 ? 2 : 1,
+                                      MODE == MODE_S2 ? 1 : MODE == MODE_T ? 1 : 0);
   p.dchunk = dchunk;
   p.nchunks = (Dm + dchunk - 1) / dchunk;
   const long items = cols * p.nchunks;

@@ -403,15 +403,11 @@ static int launch8(const float* x, const float* wpk, Params p, cudaStream_t st) 
   int cap = (tma::pow2_floor(512 / per_sm) - 8) / kG;
   if (cap > 21) cap = 21;
   if (dchunk_env > 0 && dchunk_env < cap) cap = dchunk_env;
-  // equal chunks: nchunks = ceil(D / cap), dchunk = ceil(D / nchunks)
-  int nchunks = (p.D + cap - 1) / cap;
-  int dchunk = (p.D + nchunks - 1) / nchunks;
   p.tiles_w = (p.W + kColsOut - 1) / kColsOut;
   p.tiles_h = (p.H + kRowsOut - 1) / kRowsOut;
-  // small volumes: more, shorter chunks until every resident CTA has an item
   const long cols = (long)p.B * p.tiles_w * p.tiles_h;
-  while (dchunk > 4 && cols * ((p.D + dchunk - 1) / dchunk) < (long)num_sms() * per_sm)
-    dchunk = (dchunk + 1) / 2;
+  const int dchunk =
+      tma::pick_dchunk(p.D, cap, cols, (long)num_sms() * per_sm, 1, p.planar ? 0 : 2);
   p.dchunk = dchunk;
   p.nchunks = (p.D + dchunk - 1) / dchunk;
   bool hit = false;

@@ -48,5 +48,25 @@ const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, int C, 
 
 inline int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
 
+// Depth-chunk length for the persistent kernels.  An item (tile column x depth chunk of dc
+// output groups) costs mul*dc + add input slices (+ `fixed` for pipeline fill / drain); CTA k
+// runs items k, k + resident, ...: the kernel lasts as long as the busiest CTA, i.e.
+// ceil(items / resident) items.  Long chunks amortise the depth halo, short ones fill the
+// machine and balance the last round; pick the cheapest (ties -> longer chunks).
+inline int pick_dchunk(int D, int cap, long cols, long resident, int mul, int add, int fixed = 2) {
+  if (cap > D) cap = D;
+  if (cap < 1) cap = 1;
+  if (resident < 1) resident = 1;
+  int best = cap;
+  long best_cost = -1;
+  for (int dc = cap; dc >= 1; --dc) {
+    const long items = cols * ((D + dc - 1) / dc);
+    const long rounds = (items + resident - 1) / resident;
+    const long cost = rounds * (mul * dc + add + fixed);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = dc; }
+  }
+  return best;
+}
+
 }  // namespace tma
 }  // namespace casmvs
