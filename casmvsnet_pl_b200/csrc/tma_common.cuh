@@ -1,6 +1,7 @@
 // TMA helpers shared by the TMA-fed tcgen05 convolution kernels (sm_100a only).
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -53,7 +54,15 @@ inline int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
 // runs items k, k + resident, ...: the kernel lasts as long as the busiest CTA, i.e.
 // ceil(items / resident) items.  Long chunks amortise the depth halo, short ones fill the
 // machine and balance the last round; pick the cheapest (ties -> longer chunks).
-inline int pick_dchunk(int D, int cap, long cols, long resident, int mul, int add, int fixed = 2) {
+inline int pick_dchunk(int D, int cap, long cols, long resident, int mul, int add, int fixed = -1) {
+  if (fixed < 0) {                      // CASMVS_DCHUNK_FIXED: per-item overhead in slice units
+    static int env_fixed = -1;
+    if (env_fixed < 0) {
+      const char* e = getenv("CASMVS_DCHUNK_FIXED");
+      env_fixed = e ? atoi(e) : 2;
+    }
+    fixed = env_fixed;
+  }
   if (cap > D) cap = D;
   if (cap < 1) cap = 1;
   if (resident < 1) resident = 1;

@@ -50,13 +50,18 @@ class FeatureNet(nn.Module):
     # cuDNN's heuristics pick FFT/sgemm algorithms that are several times slower here
     benchmark = True
 
-    def forward(self, x):
+    def forward(self, x, overlap=False):
+        """overlap=True (tf32 inference path only): the two finer pyramid levels are produced on a
+        side stream and the result carries "_ready" = {level: event}; the caller must make its
+        stream wait for the event before touching that level (CascadeMVSNet.forward does, so the
+        coarsest cascade stage -- many small, latency-bound kernels -- runs concurrently with the
+        bandwidth-heavy top-down half of the pyramid)."""
         with torch.backends.cudnn.flags(enabled=True, benchmark=self.benchmark,
                                         allow_tf32=self.allow_tf32):
             if self.training or torch.is_grad_enabled():
                 return self._forward_modules(x)
             if self.allow_tf32 and self.tensor_path and x.is_cuda:
-                return self._forward_tensor(x)
+                return self._forward_tensor(x, overlap)
             return self._forward_folded(x)
 
     # -- inference path: eval-mode ABN folded into the conv (w*alpha, beta') so each block
@@ -96,7 +101,7 @@ class FeatureNet(nn.Module):
             self._smooth_key = skey
         return cache, self._pack_cache, self._smooth_pack
 
-    def _forward_tensor(self, x):
+    def _forward_tensor(self, x, overlap=False):
         cache, packed, (sm0, sm1) = self._packed()
 
         def planar(t, i, keep):
@@ -114,11 +119,38 @@ class FeatureNet(nn.Module):
         c1 = planar(planar(strided(c0, 2), 3, False), 4, True)
         c2 = planar(planar(strided(c1, 5), 6, False), 7, True)
         f2 = ops.fpn_merge(None, c2, self.toplayer.weight, self.toplayer.bias)
-        m1 = ops.fpn_merge(f2, c1, self.lat1.weight, self.lat1.bias, round_tf32=True)
-        m0 = ops.fpn_merge(m1, c0, self.lat0.weight, self.lat0.bias, round_tf32=True)
-        l1 = ops.conv2d_planar(m1, sm1, 32, 16, self.smooth1.bias, 1.0, ops.TF32, keep_fp32=True)
-        l0 = ops.conv2d_planar(m0, sm0, 32, 8, self.smooth0.bias, 1.0, ops.TF32, keep_fp32=True)
-        return {"level_0": l0, "level_1": l1, "level_2": f2}
+
+        def top_down():
+            m1 = ops.fpn_merge(f2, c1, self.lat1.weight, self.lat1.bias, round_tf32=True)
+            l1 = ops.conv2d_planar(m1, sm1, 32, 16, self.smooth1.bias, 1.0, ops.TF32,
+                                   keep_fp32=True)
+            return m1, l1
+
+        def finest(m1):
+            m0 = ops.fpn_merge(m1, c0, self.lat0.weight, self.lat0.bias, round_tf32=True)
+            return ops.conv2d_planar(m0, sm0, 32, 8, self.smooth0.bias, 1.0, ops.TF32,
+                                     keep_fp32=True)
+
+        if not overlap:
+            m1, l1 = top_down()
+            return {"level_0": finest(m1), "level_1": l1, "level_2": f2}
+        main = torch.cuda.current_stream(x.device)
+        side = getattr(self, "_side_stream", None)
+        if side is None or side.device != x.device:
+            side = self._side_stream = torch.cuda.Stream(device=x.device)
+        side.wait_stream(main)                       # c0, c1, f2 are complete for the side stream
+        with torch.cuda.stream(side):
+            m1, l1 = top_down()
+            ev1 = torch.cuda.Event()
+            ev1.record(side)
+            l0 = finest(m1)
+            ev0 = torch.cuda.Event()
+            ev0.record(side)
+        for t in (l1, l0):                           # consumed on the caller's stream
+            t.record_stream(main)
+        for t in (c0, c1, f2):                       # produced on main, read on the side stream
+            t.record_stream(side)
+        return {"level_0": l0, "level_1": l1, "level_2": f2, "_ready": {1: ev1, 0: ev0}}
 
     def _forward_folded(self, x):
         x = x.contiguous(memory_format=torch.channels_last)
@@ -256,6 +288,10 @@ class CascadeMVSNet(nn.Module):
         self.interval_ratios = interval_ratios
         self.G = num_groups
         self.feature = FeatureNet(norm_act)
+        # run the top-down half of the pyramid on a side stream, concurrently with the coarsest
+        # cascade stage (tf32 inference path; CASMVS_OVERLAP=0 turns it off)
+        import os
+        self.overlap_pyramid = os.environ.get("CASMVS_OVERLAP", "1") != "0"
         for l in range(self.levels):
             cin = self.G if self.G > 1 else 8 * 2 ** l
             setattr(self, f"cost_reg_{l}", CostRegNet(cin, norm_act))
@@ -294,12 +330,17 @@ class CascadeMVSNet(nn.Module):
                 "CascadeMVSNet (B200 engine) needs CUDA inputs; there is no CPU fallback")
         results = {}
         with torch.no_grad():
-            feats = self.feature(imgs.reshape(B * V, 3, H, W))
+            feats = self.feature(imgs.reshape(B * V, 3, H, W), overlap=self.overlap_pyramid)
+            ready = feats.get("_ready", {})
+            # one re-layout for all levels instead of a strided slice copy per stage
+            proj_by_level = proj_mats.permute(2, 0, 1, 3, 4).contiguous()
             depth_l = None
             for l in reversed(range(self.levels)):
+                if l in ready:                      # level produced on the side stream
+                    torch.cuda.current_stream(imgs.device).wait_event(ready[l])
                 feats_l = feats[f"level_{l}"]
                 feats_l = feats_l.view(B, V, *feats_l.shape[1:])
-                proj_mats_l = proj_mats[:, :, l]
+                proj_mats_l = proj_by_level[l]
                 depth_interval_l = depth_interval * self.interval_ratios[l]
                 D = self.n_depths[l]
                 h, w = feats_l.shape[-2:]
