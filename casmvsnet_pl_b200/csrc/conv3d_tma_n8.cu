@@ -461,6 +461,12 @@ int conv3d_tma_n8(const float* x, const float* wpk, const float* scale, const fl
     if (Cin == 16) return tma8::launch8<16, 4, 2>(x, wpk, p, st);
     return tma8::launch8<32, 3, 2>(x, wpk, p, st);
   }
+  static int slots8 = -1;
+  if (slots8 < 0) {
+    const char* e = getenv("CASMVS_N8_SLOTS8");       // ring depth of the Cin = 8 kernels (4 or 6)
+    slots8 = e ? atoi(e) : 4;
+  }
+  if (Cin == 8 && slots8 == 6) return tma8::launch8<8, 6, 1>(x, wpk, p, st);
   if (Cin == 8) return tma8::launch8<8, 4, 1>(x, wpk, p, st);
   if (Cin == 16) return tma8::launch8<16, 4, 1>(x, wpk, p, st);
   return tma8::launch8<32, 3, 1>(x, wpk, p, st);
