@@ -28,6 +28,13 @@ for name, W, H, V, G, nd in cfgs:
         res = m(imgs, pm, dmin, dint)
     e1.record(); torch.cuda.synchronize()
     ok = all(torch.isfinite(v).all().item() for v in res.values())
+    # tcgen05 path vs the fp32 CUDA-core / cuDNN-fp32 path of the same model at this size
+    d_tf32 = res["depth_0"].clone()
+    m.set_precision("fp32")
+    ref32 = m(imgs, pm, dmin, dint)["depth_0"]
+    m.set_precision("tf32")
+    rel_l1 = ((d_tf32 - ref32).abs().mean() / ref32.abs().mean()).item()
+    del ref32
     # K1 parity at level 2 against the oracle
     with torch.no_grad():
         f = m.feature(imgs.reshape(V, 3, H, W))["level_2"]
@@ -40,7 +47,7 @@ for name, W, H, V, G, nd in cfgs:
     err = (got - want).abs().max().item()
     print(json.dumps(dict(cfg=name, W=W, H=H, V=V, G=G, n_depths=nd, finite=ok,
                           ms_per_depth_map=round(e0.elapsed_time(e1) / 5, 3),
-                          k1_level2_max_err=err, k1_level2_max_ref=want.abs().max().item(),
+                          depth0_rel_l1_tf32_vs_fp32=rel_l1, k1_level2_max_err=err, k1_level2_max_ref=want.abs().max().item(),
                           depth0_range=[res["depth_0"].min().item(), res["depth_0"].max().item()],
                           peak_mem_GB=round(torch.cuda.max_memory_allocated() / 2**30, 2))), flush=True)
     del m, res
