@@ -141,6 +141,9 @@ conv3d_tma_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   tc_fence_after();
 
   if (threadIdx.x == 0) TMA_STAMP(3, 0, 1);
+  // nothing above depends on the previous kernel of the stream (see tma_common.cuh)
+  tma::pdl_trigger();
+  tma::pdl_wait();
   bool w_ready = false;                             // MMA issuer: weight image has landed
   uint32_t gs = 0;                                  // slices processed before this item (all roles)
   int ep = 0;                                       // items processed by this CTA
@@ -407,7 +410,7 @@ static int launch(const float* x, const float* wpk, Params p, cudaStream_t st) {
   int resident = num_sms() * per_sm / nco;
   if (resident < 1) resident = 1;
   const long gx = items < resident ? items : resident;
-  kfn<<<dim3((unsigned)gx, (unsigned)nco), kThreadsTma, S::kTotal, st>>>(*map, p);
+  launch_pdl(hit, kfn, dim3((unsigned)gx, (unsigned)nco), kThreadsTma, S::kTotal, st, *map, p);
   return after_launch("conv3d_tma");
 }
 

@@ -137,6 +137,9 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   __syncthreads();
   tc_fence_after();
 
+  // nothing above depends on the previous kernel of the stream (see tma_common.cuh)
+  tma::pdl_trigger();
+  tma::pdl_wait();
   bool w_ready = false;                             // MMA issuer: weight image has landed
   uint32_t gs = 0;                                  // slices processed before this item
   int ep = 0;                                       // items processed by this CTA
@@ -505,7 +508,7 @@ static int launch2(const float* x, const float* wpk, Params p, cudaStream_t st) 
   long resident = (long)num_sms() * per_sm / nco;
   if (resident < 1) resident = 1;
   const long gx = items < resident ? items : resident;
-  kfn<<<dim3((unsigned)gx, (unsigned)nco), kThreads2, C::kTotal, st>>>(*map, p);
+  tma::launch_pdl(hit, kfn, dim3((unsigned)gx, (unsigned)nco), kThreads2, C::kTotal, st, *map, p);
   return after_launch("conv3d_tma2");
 }
 

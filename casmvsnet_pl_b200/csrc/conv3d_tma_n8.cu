@@ -162,6 +162,9 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   tc_fence_after();
 
   if (threadIdx.x == 0) N8_STAMP(3, 0, 1);
+  // nothing above depends on the previous kernel of the stream (see tma_common.cuh)
+  tma::pdl_trigger();
+  tma::pdl_wait();
   bool w_ready = false;                             // MMA issuer: weight image has landed
   uint32_t gs = 0;                                  // slices processed before this item (all roles)
   int ep = 0;                                       // items processed by this CTA
@@ -421,7 +424,7 @@ static int launch8(const float* x, const float* wpk, Params p, cudaStream_t st) 
   const long items = (long)p.B * p.nchunks * p.tiles_h * p.tiles_w;
   const long resident = (long)num_sms() * per_sm;
   const long gx = items < resident ? items : resident;
-  kfn<<<dim3((unsigned)gx), kThreads8, S::kTotal, st>>>(*map, p);
+  tma::launch_pdl(hit, kfn, dim3((unsigned)gx), kThreads8, S::kTotal, st, *map, p);
   return after_launch("conv3d_tma_n8");
 }
 

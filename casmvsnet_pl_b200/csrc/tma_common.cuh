@@ -38,6 +38,40 @@ __device__ __forceinline__ void load_image_bulk(uint32_t dst_smem, const float* 
   }
 }
 
+// Programmatic dependent launch: the kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a CTA may start while the previous
+// kernel of the stream is still draining.  Everything before pdl_wait() -- barrier init, TMEM
+// allocation, the weight-image bulk copy, parameter loads: nothing that depends on the previous
+// kernel's output -- overlaps that tail; pdl_wait() returns once the previous grid has completed
+// and its writes are visible.  pdl_trigger() lets the next kernel of the stream do the same.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// Launch helper: <<<>>> semantics plus the programmatic-serialization attribute (CASMVS_PDL=0:
+// plain stream order, in which case the two instructions above are no-ops).  allow = false on
+// the call that has just launched the weight-image builder: the prologue reads that image.
+template <typename Kernel, typename... Args>
+inline cudaError_t launch_pdl(bool allow, Kernel kfn, dim3 grid, int threads, size_t smem,
+                              cudaStream_t st, Args... args) {
+  static int pdl = -1;
+  if (pdl < 0) {
+    const char* e = getenv("CASMVS_PDL");
+    pdl = e ? atoi(e) : 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && allow) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kfn, args...);
+}
+
 // Tiled tensor map over the activation tensor x (B,D,H,W,C) viewed as {C, W, H, D, B} with box
 // {CB, box_w, box_h, 1, 1}, swizzle = CB*4 bytes (128/64/32), out-of-bounds elements zero-filled
 // (= the convolution's zero padding).  stride_w = 2: the box walks every second voxel along W
