@@ -66,3 +66,49 @@ def test_errors_are_reported_not_thrown():
     assert rc < 0 and b"divisible by 8" in lib.casmvs_last_error()
     with pytest.raises(_lib.CasMVSError):
         _lib.check(rc, "costreg")
+
+
+def _header_constants():
+    src = open(os.path.join(ROOT, "include", "casmvs.h")).read()
+    consts = {k: int(v) for k, v in re.findall(r"#define\s+(CASMVS_[A-Z0-9_]+)\s+(\d+)", src)}
+    for body in re.findall(r"enum\s+\w+\s*\{(.*?)\}", src, flags=re.S):
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        consts.update({k: int(v) for k, v in re.findall(r"(CASMVS_[A-Z0-9_]+)\s*=\s*(\d+)", body)})
+    return consts
+
+
+def test_binding_constants_match_header():
+    """The ctypes binding re-states the header's enums and flags: keep them in lock step."""
+    from casmvsnet_pl_b200 import _lib
+    c = _header_constants()
+    assert (c["CASMVS_NCHW"], c["CASMVS_NHWC"]) == (_lib.NCHW, _lib.NHWC)
+    assert (c["CASMVS_FP32"], c["CASMVS_TF32"], c["CASMVS_TF32X3"]) == (_lib.FP32, _lib.TF32, _lib.TF32X3)
+    assert (c["CASMVS_CONV"], c["CASMVS_CONV_TRANSPOSE"], c["CASMVS_CONV_PLANAR"]) == \
+        (_lib.CONV, _lib.CONV_TRANSPOSE, _lib.CONV_PLANAR)
+    assert c["CASMVS_ROUND_TF32"] == _lib.ROUND_TF32
+    assert c["CASMVS_KEEP_FP32_OUT"] == _lib.KEEP_FP32_OUT
+    # flags must not collide with the enum values they are OR-ed into
+    assert c["CASMVS_ROUND_TF32"] > max(c["CASMVS_NCHW"], c["CASMVS_NHWC"])
+    assert c["CASMVS_KEEP_FP32_OUT"] > c["CASMVS_TF32X3"]
+
+
+def test_new_entry_points_validate_arguments():
+    """FeatureNet entry points: argument validation comes before any device work."""
+    from casmvsnet_pl_b200 import _lib
+    lib = _lib.load()
+    one = ctypes.c_void_p(16)
+    rc = lib.casmvs_conv3d_fwd(one, one, None, None, 1.0, None, one, 1, 8, 8, 4, 16, 16,
+                               _lib.CONV_PLANAR, 2, _lib.TF32, None)
+    assert rc < 0 and b"stride" in lib.casmvs_last_error()
+    rc = lib.casmvs_conv3d_fwd(one, one, None, None, 1.0, None, one, 1, 8, 8, 4, 16, 16,
+                               _lib.CONV, 1, _lib.TF32 | 512, None)
+    assert rc < 0 and b"precision" in lib.casmvs_last_error()
+    rc = lib.casmvs_fpn_merge_fwd(one, one, one, one, one, 1, 15, 16, 8, 0, None)
+    assert rc < 0 and b"even" in lib.casmvs_last_error()
+    rc = lib.casmvs_fpn_merge_fwd(None, one, one, one, one, 1, 16, 16, 6, 0, None)
+    assert rc < 0 and b"multiple of 4" in lib.casmvs_last_error()
+    rc = lib.casmvs_conv2d_5x5s2_fwd(one, one, one, 0.01, one, 1, 8, 8, 32, 32, 0, None)
+    assert rc < 0 and b"8->16" in lib.casmvs_last_error()
+    rc = lib.casmvs_conv2d_rgb8_fwd(None, one, one, 0.01, one, 1, 32, 32, 0, None)
+    assert rc < 0 and b"null" in lib.casmvs_last_error()
+    assert lib.casmvs_conv2d_rgb8_fwd(one, one, one, 0.01, one, 0, 32, 32, 0, None) == 0   # empty batch
