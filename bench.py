@@ -31,6 +31,11 @@ N_DEPTHS = (8, 32, 48)          # level 0..2  (BASELINE writes coarse->fine 48/3
 RATIOS = (1, 2, 4)
 METRIC = "depth-maps/sec at 640x512 V=3 D=48/32/8"
 FALLBACK_HBM_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md fallback
+# identical in both arms (the driver compares the two lines' config.workload)
+WORKLOAD = ("cfg2: 640x512, V=3, D=48/32/8, variance cost, B=1 per GPU "
+            "(BASELINE.json configs[1])")
+K2_ALGO_BYTES = 1846.8e6        # layer-by-layer fp32 activation traffic, cfg2
+K2_ALGO_FLOP = 81.1e9           # 2*27*N*(8*Cin3d+120) summed over the three stages
 
 
 def k1_algorithmic_bytes(V, G=1, W=W_IMG, H=H_IMG, n_depths=N_DEPTHS):
@@ -84,12 +89,13 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
+                pw.append(float(r[3]))
                 for n, v in zip(names, r[4:8]):
                     if v.strip().lower().startswith("active"):
                         reasons.add(n)
@@ -97,7 +103,8 @@ class ClockSampler:
                 continue
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "reasons": sorted(reasons)}
 
 
 def cpu_port_forward_factory(threads):
@@ -146,16 +153,19 @@ def best_cpu_threads(cores):
     return best_t
 
 
-def time_cpu_port(steps, warmup, threads):
+def time_cpu_port(steps, warmup, threads, want_result=False):
     fwd = cpu_port_forward_factory(threads)
     for _ in range(warmup):
         fwd()
     ts = []
+    res = None
     for _ in range(steps):
         t0 = time.perf_counter()
-        fwd()
+        res = fwd()
         ts.append(time.perf_counter() - t0)
     ts.sort()
+    if want_result:
+        return ts[len(ts) // 2], sum(ts), res
     return ts[len(ts) // 2], sum(ts)
 
 
@@ -177,8 +187,8 @@ def run_reference_arm(args, rank):
         "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: 640x512, V=3, D=48/32/8, variance cost, B=1",
-                   "device": "cpu", "torch_threads": torch.get_num_threads()},
+        "config": {"workload": WORKLOAD, "device": "cpu",
+                   "torch_threads": torch.get_num_threads()},
         "cpu_baseline": {"value": value, "unit": "depth-maps/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "depth-maps/s", "h2d_bytes_per_step": 0,
@@ -188,6 +198,32 @@ def run_reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def pin_to_gpu_numa(local_rank):
+    """Bind this rank (and the pinned buffers it allocates afterwards) to the CPUs that
+    `nvidia-smi topo -m` lists as local to its GPU.  Best effort; returns a description."""
+    import re
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True,
+                             timeout=30).stdout
+        for line in out.splitlines():
+            toks = line.replace("\x1b[4m", "").replace("\x1b[0m", "").split()
+            if not toks or toks[0] != f"GPU{local_rank}":
+                continue
+            for t in toks[1:]:
+                if re.fullmatch(r"\d+(-\d+)?(,\d+(-\d+)?)*", t) and ("-" in t or "," in t):
+                    cpus = set()
+                    for part in t.split(","):
+                        lo, _, hi = part.partition("-")
+                        cpus.update(range(int(lo), int(hi or lo) + 1))
+                    cpus &= os.sched_getaffinity(0)
+                    if cpus:
+                        os.sched_setaffinity(0, cpus)
+                        return f"rank bound to GPU{local_rank}-local CPUs {t}"
+    except Exception as e:                                   # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+    return "not bound (no CPU affinity column)"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -195,7 +231,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("CASMVS_PRECISION", "tf32"),
-                    choices=["fp32", "tf32", "tf32x3"])
+                    choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
@@ -221,55 +257,70 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    numa = pin_to_gpu_numa(local_rank) if world > 1 else None
+
     torch.manual_seed(0)
     model = CascadeMVSNet(n_depths=list(N_DEPTHS), interval_ratios=list(RATIOS), norm_act=ABN,
                           precision=args.precision)
     synth.randomize_model_(model, 0)
-    model = model.eval().to(dev)
+    model = model.eval().to(dev).requires_grad_(False)
     B = 1
+    K = args.steps
     imgs_h, pm_h, dmin, dint = synth.make_inputs(B=B, V=VIEWS, W=W_IMG, H=H_IMG, seed=rank)
     imgs_h, pm_h = imgs_h.pin_memory(), pm_h.pin_memory()
     imgs_d, pm_d = imgs_h.to(dev), pm_h.to(dev)
-    gather_buf = [torch.empty(B, H_IMG, W_IMG, device=dev) for _ in range(world)] if world > 1 else None
+    # multi-GPU: every rank keeps the depth maps of its own views on the device and the path's
+    # single collective gathers them ONCE, at the end of the timed region
+    nkeep = max(K, args.warmup, 3)
+    store = torch.empty(nkeep * B, H_IMG, W_IMG, device=dev) if world > 1 else None
+    gathered = torch.empty(world * nkeep * B, H_IMG, W_IMG, device=dev) if world > 1 else None
 
     graphed = None
     if not args.no_graph:
         from casmvsnet_pl_b200.graph import GraphedCascade
         graphed = GraphedCascade(model, imgs_d, pm_d, dmin, dint)
 
-    def step_resident():
-        res = graphed() if graphed is not None else model(imgs_d, pm_d, dmin, dint)
+    def gather_all(steps):
+        dist.all_gather_into_tensor(gathered[: world * steps * B], store[: steps * B])
+
+    def run_resident(steps):
+        res = None
+        with torch.no_grad():
+            for k in range(steps):
+                res = graphed() if graphed is not None else model(imgs_d, pm_d, dmin, dint)
+                if world > 1:
+                    store[k * B:(k + 1) * B].copy_(res["depth_0"])
         if world > 1:
-            dist.all_gather(gather_buf, res["depth_0"])     # the path's only collective (§8e)
+            gather_all(steps)
         return res
 
     out_depth_h = torch.empty(B, H_IMG, W_IMG).pin_memory()
     out_conf_h = torch.empty(B, H_IMG // 4, W_IMG // 4).pin_memory()
 
-    def step_e2e():
-        if graphed is not None:
-            res = graphed(imgs_h, pm_h)                          # H2D into the static buffers
-        else:
-            res = model(imgs_h.to(dev, non_blocking=True), pm_h.to(dev, non_blocking=True),
-                        dmin, dint)
-        if world > 1:
-            dist.all_gather(gather_buf, res["depth_0"])
-        out_depth_h.copy_(res["depth_0"], non_blocking=True)     # what eval.py:224-226 reads back
-        out_conf_h.copy_(res["confidence_2"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return res
-
     pipe = None
-    if graphed is not None and world == 1:
+    if graphed is not None:
         from casmvsnet_pl_b200.graph import PipelinedCascade
         pipe = PipelinedCascade(model, imgs_d, pm_d, dmin, dint)
 
-    def run_e2e_pipelined(steps):
-        # every step: H2D of that step's inputs from pinned memory, forward, D2H of its results;
-        # copies of neighbouring steps overlap the compute (two slots)
-        for _ in range(steps):
-            pipe.submit(imgs_h, pm_h)
-        pipe.drain()
+    def run_e2e(steps):
+        # every step: H2D of that step's inputs from pinned memory, forward, D2H of its results
+        if pipe is not None:
+            # copies of neighbouring steps overlap the compute (two slots), on every rank
+            for k in range(steps):
+                pipe.submit(imgs_h, pm_h, keep=store[k * B:(k + 1) * B] if world > 1 else None)
+            pipe.drain()
+        else:
+            with torch.no_grad():
+                for k in range(steps):
+                    res = model(imgs_h.to(dev, non_blocking=True), pm_h.to(dev, non_blocking=True),
+                                dmin, dint)
+                    if world > 1:
+                        store[k * B:(k + 1) * B].copy_(res["depth_0"])
+                    out_depth_h.copy_(res["depth_0"], non_blocking=True)   # eval.py:224-226
+                    out_conf_h.copy_(res["confidence_2"], non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+        if world > 1:
+            gather_all(steps)
 
     def barrier():
         if world > 1:
@@ -277,11 +328,11 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """barrier + sync | CUDA events around fn(steps) | barrier + sync; max over ranks."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        fn(steps)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -289,32 +340,41 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for _ in range(args.warmup):
-        step_resident()
-    for _ in range(2):
-        step_e2e()
+    run_resident(args.warmup)
+    run_e2e(3)
     torch.cuda.synchronize()
 
+    fb0 = _lib.fallback_count()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     n0 = _lib.launch_count()
-    ms_total = timed(step_resident, args.steps)
+    ms_total = timed(run_resident, K)
     launches = _lib.launch_count() - n0
     if graphed is not None:      # graph replays launch the captured libcasmvs kernels
-        launches += graphed.kernels_per_replay * args.steps
-    if pipe is not None:
-        run_e2e_pipelined(3)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        run_e2e_pipelined(args.steps)        # drain() waits for the last D2H
-        e1.record()
-        torch.cuda.synchronize()
-        ms_e2e = e0.elapsed_time(e1)
-    else:
-        ms_e2e = timed(step_e2e, args.steps)
+        launches += graphed.kernels_per_replay * K
+    ms_e2e = timed(run_e2e, K)
     clocks = sampler.stop() if sampler else None
+
+    # ---- sustained: the same resident step back to back for >= 2 s (clocks settle below boost)
+    sus_sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sus_sampler:
+        sus_sampler.start()
+    chunk = max(50, int(0.25 / max(ms_total / K * 1e-3, 1e-6)))
+    sus_steps, sus_ms = 0, 0.0
+    while sus_ms < 2000.0:
+        sus_ms += timed(lambda n: [graphed() if graphed is not None
+                                   else model(imgs_d, pm_d, dmin, dint) for _ in range(n)], chunk)
+        sus_steps += chunk
+    sus_clocks = sus_sampler.stop() if sus_sampler else None
+    sustained = None
+    if rank == 0:
+        sustained = {"seconds": sus_ms * 1e-3, "steps": sus_steps,
+                     "depth_maps_per_s": world * B * sus_steps / (sus_ms * 1e-3),
+                     "sm_mhz_median": sus_clocks["sm_mhz"], "power_w_max": sus_clocks["power_w_max"],
+                     "reasons": sus_clocks["reasons"],
+                     "what": "CUDA-graph replays of the resident step back to back, no collective"}
+    fallbacks = _lib.fallback_count() - fb0
 
     # ---- K1 roofline: the three launches of one depth map, CUDA events, L2 flushed ----
     roofline = None
@@ -387,11 +447,74 @@ def main():
         hot = {"ms_per_depth_map": hot_ms, "depth_maps_per_s": 1e3 / hot_ms,
                "what": "features resident -> depth/confidence (K4,K1,K2,K3 x 3 stages), no FeatureNet"}
 
+    # ---- K2 roofline: the three CostRegNet stacks (11 layers each), CUDA events, L2 flushed
+    roofline_k2 = None
+    if rank == 0:
+        stage_ms = []
+        with torch.no_grad():
+            for l in (2, 1, 0):
+                f = feats[f"level_{l}"]
+                f = f.view(B, VIEWS, *f.shape[1:])
+                D = N_DEPTHS[l]
+                h, w = f.shape[-2:]
+                dv = ops.uniform_hypotheses(dmin + 3.0 * l, dint * RATIOS[l], D, B, h, w, dev)
+                cost = ops.warp_cost(f, pm_d[:, :, l].contiguous(), dv, 1, ops.NHWC,
+                                     round_tf32=(args.precision == "tf32"))
+                reg = getattr(model, f"cost_reg_{l}")
+                ts = []
+                for it in range(3 + 10):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    reg(cost)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if it >= 3:
+                        ts.append(e0.elapsed_time(e1))
+                stage_ms.append(sum(ts) / len(ts))
+                del cost
+        k2_ms = sum(stage_ms)
+        roofline_k2 = {"kernel": "CostRegNet x3 (33 tcgen05 conv launches / depth map)",
+                       "algorithmic_bytes": K2_ALGO_BYTES, "flop": K2_ALGO_FLOP, "ms": k2_ms,
+                       "per_stage_ms": dict(zip(("level_2", "level_1", "level_0"), stage_ms)),
+                       "GBps": K2_ALGO_BYTES / (k2_ms * 1e-3) / 1e9,
+                       "frac_hbm": K2_ALGO_BYTES / (k2_ms * 1e-3) / 1e9 / peak,
+                       "TFLOPps": K2_ALGO_FLOP / (k2_ms * 1e-3) / 1e12,
+                       "bound": "hbm (fp32 activations, Cout <= 64: 44 FLOP/B << ridge)",
+                       "tensor_pipe_pct": None,
+                       "l2": "flushed before every timed stack"}
+        prof = os.path.join(ROOT, "profiles", "k2_tensor_pipe.json")
+        if os.path.isfile(prof):
+            try:
+                roofline_k2["tensor_pipe_pct"] = json.load(open(prof))
+            except Exception:
+                pass
+
     cpu_baseline = None
+    parity = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         avail = len(os.sched_getaffinity(0))
         cores = best_cpu_threads(avail)
-        med, total = time_cpu_port(3, 1, cores)
+        med, total, ref_out = time_cpu_port(3, 1, cores, want_result=True)
+        # parity of THIS run's GPU output against the oracle on the same seed-0 inputs/weights
+        with torch.no_grad():
+            got = graphed() if graphed is not None else model(imgs_d, pm_d, dmin, dint)
+        torch.cuda.synchronize()
+        parity = {}
+        for l in (2, 1, 0):
+            d, r = got[f"depth_{l}"].cpu(), ref_out[f"depth_{l}"]
+            parity[f"rel_l1_depth_{l}"] = ((d - r).abs().mean() / r.abs().mean()).item()
+        gen = torch.Generator().manual_seed(1)
+        gt = ref_out["depth_0"] + 5.6 * torch.randn(ref_out["depth_0"].shape, generator=gen)
+        a = (got["depth_0"].cpu() - gt).abs().mean().item()
+        b = (ref_out["depth_0"] - gt).abs().mean().item()
+        parity.update({"rel_l1": parity["rel_l1_depth_0"], "abs_err_ours_mm": a,
+                       "abs_err_oracle_mm": b, "abs_err_delta": abs(a - b),
+                       "confidence_2_max_delta": (got["confidence_2"].cpu() -
+                                                  ref_out["confidence_2"]).abs().max().item(),
+                       "against": "oracle.cascade_forward on the same seed-0 inputs and weights "
+                                  "(the cpu_baseline run)", "tolerance": "rel_l1 < 1e-3 (north_star)"})
+        assert parity["rel_l1"] < 1e-3, parity
         cpu_baseline = {"value": 1.0 / med, "unit": "depth-maps/s", "cores": cores, "kind": "port",
                         "sample": "1 warm-up + 3 timed full forwards of the same cfg2 workload "
                                   f"(median {med:.2f} s/depth-map), oracle port of the reference "
@@ -409,15 +532,16 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.precision == "fp32" else f"f32 (conv products {args.precision}, fp32 accumulate)",
             "data": "synthetic",
-            "config": {"workload": "cfg2: 640x512, V=3, D=48/32/8, variance cost, B=1 per GPU "
-                                   "(BASELINE.json configs[1])",
+            "config": {"workload": WORKLOAD,
                        "step": ("CascadeMVSNet.forward = FeatureNet (cuDNN fp32 convs + fused FPN "
                                 "kernel) + 3 cascade stages") if args.precision == "fp32" else
                                ("CascadeMVSNet.forward = FeatureNet (own kernels: planar tcgen05 "
                                 "convs, RGB block, FPN merges) + 3 cascade stages (K4, K1, K2 x 11 "
                                 "layers on tcgen05, K3)"),
-                       "parallelism": f"dp{world} (independent reference views per rank, one "
-                                      "all_gather of depth_0 per step)" if world > 1 else "single GPU",
+                       "parallelism": f"dp{world} (independent reference views per rank; ONE "
+                                      f"all_gather_into_tensor of all {args.steps} per-rank depth maps "
+                                      "at the end of the timed region)" if world > 1 else "single GPU",
+                       "numa": numa,
                        "precision": args.precision,
                        "cuda_graph": not args.no_graph,
                        "l2": "per-step working set (>1 GB of intermediates) exceeds the 126 MB L2; "
@@ -429,6 +553,10 @@ def main():
                             "confidence_2, every step; copies of neighbouring steps overlap compute "
                             "(2-slot pipeline)") if pipe is not None else
                            "pinned host inputs -> H2D -> forward -> D2H, serial"},
+            "parity": parity,
+            "fallbacks": fallbacks,
+            "sustained": sustained,
+            "roofline_k2": roofline_k2,
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
@@ -436,6 +564,7 @@ def main():
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
+    assert fallbacks == 0, f"{fallbacks} tf32 layers fell back to the CUDA-core kernel"
     if world > 1:
         dist.destroy_process_group()
 

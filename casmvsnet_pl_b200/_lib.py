@@ -13,9 +13,9 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libcasmvs.so")
 NCHW, NHWC = 0, 1
 ROUND_TF32 = 256
 KEEP_FP32_OUT = 256      # OR-ed into conv3d precision
-FP32, TF32, TF32X3 = 0, 1, 2
+FP32, TF32 = 0, 1
 CONV, CONV_TRANSPOSE, CONV_PLANAR = 0, 1, 2
-PRECISIONS = {"fp32": FP32, "tf32": TF32, "tf32x3": TF32X3}
+PRECISIONS = {"fp32": FP32, "tf32": TF32}
 
 # name -> (restype, argtypes); must list every symbol include/casmvs.h declares
 SIGNATURES = {
@@ -23,6 +23,9 @@ SIGNATURES = {
     "casmvs_last_error": (c_char_p, []),
     "casmvs_device_check": (c_int, [c_int]),
     "casmvs_launch_count": (c_uint64, []),
+    "casmvs_fallback_count": (c_uint64, []),
+    "casmvs_release_weight_images": (c_int, [c_void_p, c_size_t]),
+    "casmvs_weight_cache_generation": (c_uint64, []),
     "casmvs_warp_cost_workspace_bytes": (c_size_t, [c_int] * 6),
     "casmvs_warp_cost_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                      c_int, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -92,3 +95,13 @@ def check(rc, what=""):
 
 def launch_count():
     return int(load().casmvs_launch_count())
+
+
+def fallback_count():
+    """tf32-mode layers that ran on the CUDA-core kernel because no tcgen05 kernel covers
+    their shape (0 for the reference architecture)."""
+    return int(load().casmvs_fallback_count())
+
+
+def weight_cache_generation():
+    return int(load().casmvs_weight_cache_generation())

@@ -8,6 +8,7 @@
 namespace casmvs {
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_fallbacks{0};
 static thread_local char t_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -21,10 +22,6 @@ void set_error(const char* fmt, ...) {
 int conv3d_direct(const float* x, const float* wpk, const float* scale, const float* shift,
                   float slope, const float* skip, float* y, int B, int Cin, int Cout, int D,
                   int h, int w, int kind, int stride, cudaStream_t st, int round_out);
-// conv3d_tc.cu (tcgen05): returns 1 if this layer shape is not handled by the tensor path
-int conv3d_tc(const float* x, const float* wpk, const float* scale, const float* shift,
-              float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
-              int w, int kind, int stride, int precision, cudaStream_t st);
 // conv3d_tma.cu (tcgen05 + TMA producer, persistent: the default stride-1 tensor path)
 int conv3d_tma(const float* x, const float* wpk, const float* scale, const float* shift,
                float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
@@ -33,20 +30,10 @@ int conv3d_tma(const float* x, const float* wpk, const float* scale, const float
 int conv3d_tma_n8(const float* x, const float* wpk, const float* scale, const float* shift,
                   float slope, const float* skip, float* y, int B, int Cin, int Cout, int D,
                   int h, int w, int kind, int stride, int precision, cudaStream_t st);
-// conv3d_tc3.cu (tcgen05, stride-1 layers with Cout <= 8: kd and kh folded into N)
-int conv3d_tc3(const float* x, const float* wpk, const float* scale, const float* shift,
-               float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
-               int w, int kind, int stride, int precision, cudaStream_t st);
 // conv3d_tma2.cu (tcgen05 + TMA producer, persistent: stride-2 and transposed layers)
 int conv3d_tma2(const float* x, const float* wpk, const float* scale, const float* shift,
                 float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
                 int w, int kind, int stride, int precision, cudaStream_t st);
-// conv3d_tc2.cu (tcgen05, stride-2 and transposed layers)
-int conv3d_tc2(const float* x, const float* wpk, const float* scale, const float* shift,
-               float slope, const float* skip, float* y, int B, int Cin, int Cout, int D, int h,
-               int w, int kind, int stride, int precision, cudaStream_t st);
-
-namespace tc { void image_cache_clear(); }
 
 struct LayerSpec { int cin, cout, kind, stride; };
 
@@ -69,11 +56,7 @@ extern "C" int casmvs_version(void) { return CASMVS_VERSION; }
 extern "C" const char* casmvs_last_error(void) { return t_err; }
 extern "C" uint64_t casmvs_launch_count(void) { return g_launches.load(); }
 
-extern "C" int casmvs_invalidate_weight_cache(void) {
-  cudaDeviceSynchronize();
-  casmvs::tc::image_cache_clear();
-  return 0;
-}
+extern "C" uint64_t casmvs_fallback_count(void) { return g_fallbacks.load(); }
 
 extern "C" int casmvs_device_check(int device) {
   int n = 0;
@@ -108,34 +91,27 @@ extern "C" int casmvs_conv3d_fwd(const float* x, const float* w_packed, const fl
                  "conv3d: unsupported stride %d", stride);
   const int flags = precision & ~0xff;
   precision &= 0xff;
-  CASMVS_REQUIRE(precision >= CASMVS_FP32 && precision <= CASMVS_TF32X3 &&
-                     (flags & ~CASMVS_KEEP_FP32_OUT) == 0, "conv3d: bad precision");
+  CASMVS_REQUIRE((precision == CASMVS_FP32 || precision == CASMVS_TF32) &&
+                     (flags & ~CASMVS_KEEP_FP32_OUT) == 0, "conv3d: bad precision %d", precision);
   if (B == 0) return 0;
   cudaStream_t st = as_stream(stream);
-  if (precision != CASMVS_FP32) {
+  if (precision == CASMVS_TF32) {
     const int pf = precision | flags;
-    int rc = 1;
-    if (kind != CASMVS_CONV_PLANAR)
-      rc = conv3d_tc3(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
-                      stride, precision, st);
-    if (rc <= 0) return rc;  // handled (0) or failed (<0); 1 = shape not covered
-    rc = conv3d_tma_n8(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
-                       stride, pf, st);
+    // tcgen05 kernels: each returns 0 (handled), <0 (failed) or 1 (shape not covered)
+    int rc = conv3d_tma_n8(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
+                           stride, pf, st);
     if (rc <= 0) return rc;
     rc = conv3d_tma(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
                     stride, pf, st);
     if (rc <= 0) return rc;
     if (kind != CASMVS_CONV_PLANAR) {
-      rc = conv3d_tc(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
-                     stride, precision, st);
-      if (rc <= 0) return rc;
       rc = conv3d_tma2(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
                        stride, precision, st);
       if (rc <= 0) return rc;
-      rc = conv3d_tc2(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
-                      stride, precision, st);
-      if (rc <= 0) return rc;  // 1 = shape not covered -> CUDA cores
     }
+    // no tensor-core kernel covers this layer shape: it runs on the CUDA cores (same TF32-rounded
+    // storage convention).  Counted, so callers can assert the fast path was taken.
+    g_fallbacks.fetch_add(1, std::memory_order_relaxed);
   }
   // in the tf32 modes every stored activation is tf32-rounded (unbiased operand for
   // the tensor-core layers); the prob head (Cout == 1) feeds the softmax and stays fp32

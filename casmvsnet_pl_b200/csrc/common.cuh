@@ -16,6 +16,8 @@ namespace casmvs {
 // thread-local error string + process-wide launch counter (api.cu)
 void set_error(const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
+// tensor-core-mode layers that ended on the CUDA-core kernel (casmvs_fallback_count)
+extern std::atomic<uint64_t> g_fallbacks;
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -38,15 +40,37 @@ inline int after_launch(const char* what) {
     }                                    \
   } while (0)
 
+// Host-side state is kept per device ordinal: cudaFuncSetAttribute and the SM count are
+// per-device properties, and a process may drive several GPUs (model.to("cuda:1")).
+constexpr int kMaxDevices = 64;
+inline int cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
 inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static std::atomic<int> n[kMaxDevices];
+  const int dev = cur_device();
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (v <= 0) v = 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize opt-in, once per (kernel, device)
+template <typename K>
+inline int opt_in_smem(K kfn, int bytes, std::atomic<bool> (&done)[kMaxDevices], const char* what) {
+  const int dev = cur_device();
+  if (done[dev].load(std::memory_order_acquire)) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cannot opt in to %d B of shared memory: %s", what, bytes, cudaGetErrorString(e));
+    return -2;
+  }
+  done[dev].store(true, std::memory_order_release);
+  return 0;
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) {

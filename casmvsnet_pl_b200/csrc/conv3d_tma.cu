@@ -29,6 +29,8 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <mutex>
+
 #include "tma_common.cuh"
 
 namespace casmvs {
@@ -319,19 +321,50 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 
+// Generic tiled-map encoder for other kernels of the library (K1's feature boxes): fp32
+// elements, rank <= 5, zero fill out of bounds.  0 on success.
+int encode_tiled(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  auto enc = encode_fn();
+  if (!enc) { set_error("tma: cuTensorMapEncodeTiled is not available"); return -2; }
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                      : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                         const_cast<void*>(base), gdim, gstr, bx, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tma: cuTensorMapEncodeTiled failed (%d), rank %d", (int)r, rank);
+    return -2;
+  }
+  return 0;
+}
+
 // Tensor maps are pure functions of (pointer, shape, box): memoised, since inference calls
 // every layer with the same workspace pointers each step.
 struct MapEntry { const void* x; int B, D, H, W, C, CB, bw, bh, sw; CUtensorMap map; };
 static MapEntry g_maps[128];
 static int g_maps_n = 0, g_maps_next = 0;
+static std::mutex g_maps_mu;
 
 const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, int C, int CB, int box_w,
                              int box_h, int stride_w) {
+  // the returned map is a per-thread copy: ring slots may be recycled by other threads
+  static thread_local CUtensorMap t_ret;
+  std::lock_guard<std::mutex> lock(g_maps_mu);
   for (int i = 0; i < g_maps_n; ++i) {
     const MapEntry& e = g_maps[i];
     if (e.x == x && e.B == B && e.D == D && e.H == H && e.W == W && e.C == C && e.CB == CB &&
-        e.bw == box_w && e.bh == box_h && e.sw == stride_w)
-      return &e.map;
+        e.bw == box_w && e.bh == box_h && e.sw == stride_w) {
+      t_ret = e.map;
+      return &t_ret;
+    }
   }
   auto enc = encode_fn();
   if (!enc) { set_error("conv3d_tma: cuTensorMapEncodeTiled is not available"); return nullptr; }
@@ -357,7 +390,8 @@ const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, int C, 
     return nullptr;
   }
   e.x = x; e.B = B; e.D = D; e.H = H; e.W = W; e.C = C; e.CB = CB; e.bw = box_w; e.bh = box_h; e.sw = stride_w;
-  return &e.map;
+  t_ret = e.map;
+  return &t_ret;
 }
 
 
@@ -365,17 +399,8 @@ template <int CIN, int GW, int SLOTS>
 static int launch(const float* x, const float* wpk, Params p, cudaStream_t st) {
   using S = Smem<CIN, GW, SLOTS>;
   auto kfn = conv3d_tma_kernel<CIN, GW, SLOTS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         S::kTotal);
-    if (e != cudaSuccess) {
-      set_error("conv3d_tma: cannot opt in to %d B of shared memory: %s", S::kTotal,
-                cudaGetErrorString(e));
-      return -2;
-    }
-    attr_set = true;
-  }
+  static std::atomic<bool> attr_set[kMaxDevices];
+  if (int rc = opt_in_smem(kfn, S::kTotal, attr_set, "conv3d_tma")) return rc;
   const CUtensorMap* map = input_map(x, p.B, p.D, p.H, p.W, CIN, S::CB, kHaloW, kHaloH);
   if (!map) return -2;
   // resident CTAs per SM by shared memory (1 KB per CTA is reserved by the system); the TMEM
@@ -399,18 +424,18 @@ static int launch(const float* x, const float* wpk, Params p, cudaStream_t st) {
   if (dchunk_env > 0 && dchunk_env <= cap) dchunk = dchunk_env < p.D ? dchunk_env : p.D;
   p.dchunk = dchunk;
   p.nchunks = (p.D + dchunk - 1) / dchunk;
-  bool hit = false;
-  float* img = image_cache_lookup(wpk, 1000 + CIN * 100 + GW, (size_t)S::kWBytes * nco, &hit);
-  if (!img) { set_error("conv3d_tma: cannot allocate the weight image"); return -2; }
-  if (!hit) {
-    if (int rc = build_stride1_image(wpk, img, CIN, GW, p.Cout, p.cout_total, st)) return rc;
+  const ImageRef ir = image_cache_get(wpk, 1000 + CIN * 100 + GW, (size_t)S::kWBytes * nco, st);
+  if (!ir.img) return -2;
+  if (!ir.hit) {
+    if (int rc = build_stride1_image(wpk, ir.img, CIN, GW, p.Cout, p.cout_total, st)) return rc;
+    image_cache_built(ir.img, st);
   }
-  p.bimg = img;
+  p.bimg = ir.img;
   const long items = (long)p.B * p.nchunks * p.tiles_h * p.tiles_w;
   int resident = num_sms() * per_sm / nco;
   if (resident < 1) resident = 1;
   const long gx = items < resident ? items : resident;
-  launch_pdl(hit, kfn, dim3((unsigned)gx, (unsigned)nco), kThreadsTma, S::kTotal, st, *map, p);
+  launch_pdl(ir.settled, kfn, dim3((unsigned)gx, (unsigned)nco), kThreadsTma, S::kTotal, st, *map, p);
   return after_launch("conv3d_tma");
 }
 

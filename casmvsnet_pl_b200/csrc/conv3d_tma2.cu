@@ -451,17 +451,8 @@ static int launch2(const float* x, const float* wpk, Params p, cudaStream_t st) 
   using C = Cfg<MODE, CIN, COUT>;
   static_assert(C::kTotal <= 227 * 1024, "shared memory budget");
   auto kfn = conv3d_tma2_kernel<MODE, CIN, COUT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::kTotal);
-    if (e != cudaSuccess) {
-      set_error("conv3d_tma2: cannot opt in to %d B of shared memory: %s", C::kTotal,
-                cudaGetErrorString(e));
-      return -2;
-    }
-    attr_set = true;
-  }
+  static std::atomic<bool> attr_set[kMaxDevices];
+  if (int rc = opt_in_smem(kfn, C::kTotal, attr_set, "conv3d_tma2")) return rc;
   // S2: box {CB, 17 traversed -> 9 loaded, 33, 1, 1} walking W with stride 2; T: {CB, 9, 17}
   // P5: box {CB, 19 traversed -> 10 loaded, 35, 1, 1} walking W with stride 2
   const CUtensorMap* map =
@@ -493,22 +484,23 @@ static int launch2(const float* x, const float* wpk, Params p, cudaStream_t st) 
   p.dchunk = dchunk;
   p.nchunks = (Dm + dchunk - 1) / dchunk;
   const long items = cols * p.nchunks;
-  bool hit = false;
-  float* img = image_cache_lookup(wpk, 2000 + MODE * 10000 + CIN * 100 + COUT,
-                                  (size_t)C::kWBytes * nco, &hit);
-  if (!img) { set_error("conv3d_tma2: cannot allocate the weight image"); return -2; }
-  if (!hit) {
+  const ImageRef ir = image_cache_get(wpk, 2000 + MODE * 10000 + CIN * 100 + COUT,
+                                      (size_t)C::kWBytes * nco, st);
+  float* img = ir.img;
+  if (!img) return -2;
+  if (!ir.hit) {
     if constexpr (MODE == MODE_P5)
       build_image_p5_kernel<CIN, COUT><<<32, 256, 0, st>>>(wpk, img);
     else
       build_image_tma2_kernel<MODE, CIN, COUT><<<64, 256, 0, st>>>(wpk, img, p.Cout);
     if (int rc = after_launch("conv3d_tma2/build_image")) return rc;
+    image_cache_built(img, st);
   }
   p.bimg = img;
   long resident = (long)num_sms() * per_sm / nco;
   if (resident < 1) resident = 1;
   const long gx = items < resident ? items : resident;
-  tma::launch_pdl(hit, kfn, dim3((unsigned)gx, (unsigned)nco), kThreads2, C::kTotal, st, *map, p);
+  tma::launch_pdl(ir.settled, kfn, dim3((unsigned)gx, (unsigned)nco), kThreads2, C::kTotal, st, *map, p);
   return after_launch("conv3d_tma2");
 }
 

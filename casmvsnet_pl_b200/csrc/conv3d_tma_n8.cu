@@ -365,17 +365,8 @@ static int launch8(const float* x, const float* wpk, Params p, cudaStream_t st) 
   using S = Smem<CIN, SLOTS>;
   constexpr int kThreads8 = (4 * SETS + 2) * 32;
   auto kfn = conv3d_tma_n8_kernel<CIN, SLOTS, SETS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         S::kTotal);
-    if (e != cudaSuccess) {
-      set_error("conv3d_tma_n8: cannot opt in to %d B of shared memory: %s", S::kTotal,
-                cudaGetErrorString(e));
-      return -2;
-    }
-    attr_set = true;
-  }
+  static std::atomic<bool> attr_set[kMaxDevices];
+  if (int rc = opt_in_smem(kfn, S::kTotal, attr_set, "conv3d_tma_n8")) return rc;
   const CUtensorMap* map = tma::input_map(x, p.B, p.D, p.H, p.W, CIN, CIN, kBW, kBH);
   if (!map) return -2;
   static int per_sm_env = -1, dchunk_env = -1;
@@ -413,18 +404,19 @@ static int launch8(const float* x, const float* wpk, Params p, cudaStream_t st) 
       tma::pick_dchunk(p.D, cap, cols, (long)num_sms() * per_sm, 1, p.planar ? 0 : 2);
   p.dchunk = dchunk;
   p.nchunks = (p.D + dchunk - 1) / dchunk;
-  bool hit = false;
-  float* img = image_cache_lookup(wpk, 8000 + CIN + (p.planar ? 500 : 0), (size_t)S::kWBytes, &hit);
-  if (!img) { set_error("conv3d_tma_n8: cannot allocate the weight image"); return -2; }
-  if (!hit) {
+  const ImageRef ir = image_cache_get(wpk, 8000 + CIN + (p.planar ? 500 : 0), (size_t)S::kWBytes, st);
+  float* img = ir.img;
+  if (!img) return -2;
+  if (!ir.hit) {
     build_image_n8_kernel<<<32, 256, 0, st>>>(wpk, img, CIN, p.Cout, p.planar);
     if (int rc = after_launch("conv3d_tma_n8/build_image")) return rc;
+    image_cache_built(img, st);
   }
   p.bimg = img;
   const long items = (long)p.B * p.nchunks * p.tiles_h * p.tiles_w;
   const long resident = (long)num_sms() * per_sm;
   const long gx = items < resident ? items : resident;
-  tma::launch_pdl(hit, kfn, dim3((unsigned)gx), kThreads8, S::kTotal, st, *map, p);
+  tma::launch_pdl(ir.settled, kfn, dim3((unsigned)gx), kThreads8, S::kTotal, st, *map, p);
   return after_launch("conv3d_tma_n8");
 }
 

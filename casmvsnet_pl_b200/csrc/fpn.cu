@@ -405,12 +405,12 @@ extern "C" int casmvs_fpn_level_fwd(const float* prev, const float* c, const flo
   const size_t smem = (size_t)(kFpnHalo * kFpnHalo * kFpnPix + 9 * kFpnC * COUT + CLAT * kFpnC) * 4;
   cudaStream_t st = as_stream(stream);
   if (COUT == 8) {
-    static bool a = false;
-    if (!a) { cudaFuncSetAttribute(fpn_level_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); a = true; }
+    static std::atomic<bool> a[kMaxDevices];
+    if (int rc = opt_in_smem(fpn_level_kernel<8>, 100 * 1024, a, "fpn_level")) return rc;
     fpn_level_kernel<8><<<grd, 256, smem, st>>>(prev, c, lat_w, lat_b, smooth_w, smooth_b, feat_out, out, h, w, CLAT);
   } else {
-    static bool a = false;
-    if (!a) { cudaFuncSetAttribute(fpn_level_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); a = true; }
+    static std::atomic<bool> a[kMaxDevices];
+    if (int rc = opt_in_smem(fpn_level_kernel<16>, 100 * 1024, a, "fpn_level")) return rc;
     fpn_level_kernel<16><<<grd, 256, smem, st>>>(prev, c, lat_w, lat_b, smooth_w, smooth_b, feat_out, out, h, w, CLAT);
   }
   return after_launch("fpn_level");

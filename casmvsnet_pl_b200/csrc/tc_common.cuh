@@ -183,19 +183,16 @@ __device__ __forceinline__ void init_barriers(uint32_t bar_full, uint32_t bar_em
   if (t < 2 * slots + 32) fence_barrier_init();
 }
 
-// Library-owned scratch for the per-launch B operand images (built by a tiny prologue
-// kernel from the caller's packed weights, then read by every CTA with coalesced
-// cp.async instead of a 4-byte gather per CTA).  A ring of slots so that back-to-back
-// layers on one stream never alias; allocated on first use (run one warm-up forward
-// before capturing a CUDA graph).
-float* image_scratch(size_t bytes);
-// Persistent cache of built images keyed by (packed-weight pointer, kernel tag): inference
-// re-uses the same weights every call, so the prologue kernel runs once per layer.
-// casmvs_invalidate_weight_cache() must be called when packed weights are rewritten in place
-// or their buffer is freed (the Python binding does so whenever it re-packs parameters).
-float* image_cache_lookup(const void* wpk, int tag, size_t bytes, bool* hit);
+// Persistent cache of built B-operand images keyed by (packed-weight pointer, kernel tag,
+// size) -- weight_image.cu.  `hit`: the image exists (no build needed; if it was built on a
+// different stream this stream has been ordered after the build).  `settled`: the build is
+// known to have completed, so a programmatic-dependent-launch prologue may read the image.
+// On a miss the caller launches its builder kernel on `st` and then calls image_cache_built.
+struct ImageRef { float* img; bool hit; bool settled; };
+ImageRef image_cache_get(const void* wpk, int tag, size_t bytes, cudaStream_t st);
+void image_cache_built(const float* img, cudaStream_t st);
 // B operand image of the stride-1 kernels: [chunk][kh][kw][CIN/4][3*GW][4], tf32-rounded,
-// column group g holds the weights of kd = 2 - g (shared by conv3d_tc.cu and conv3d_tma.cu)
+// column group g holds the weights of kd = 2 - g (weight_image.cu)
 int build_stride1_image(const float* wpk, float* img, int CIN, int GW, int chunk, int cout_total,
                         cudaStream_t st);
 

@@ -81,6 +81,21 @@ inline cudaError_t launch_pdl(bool allow, Kernel kfn, dim3 grid, int threads, si
 const CUtensorMap* input_map(const float* x, int B, int D, int H, int W, int C, int CB, int box_w,
                              int box_h, int stride_w = 1);
 
+// Generic fp32 tiled map (rank <= 5, unit element strides, zero fill out of bounds); dims /
+// box innermost first, strides_bytes for dims 1..rank-1.  0 on success.  (conv3d_tma.cu)
+int encode_tiled(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3)
+      : "memory");
+}
+
 inline int pow2_floor(int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; }
 
 // Depth-chunk length for the persistent kernels.  An item (tile column x depth chunk of dc

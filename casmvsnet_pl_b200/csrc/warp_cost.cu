@@ -15,11 +15,10 @@
 // once.  The kernel is write-bound.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "k1_common.cuh"
 
 namespace casmvs {
 
-constexpr int kCPT = 8;          // channels per thread
 constexpr int kMaxSrc = 15;      // V-1 supported by the smem projection table
 constexpr int kK1Threads = 128;
 
@@ -73,90 +72,6 @@ __device__ __forceinline__ void blend8(const float* __restrict__ base, const Tap
   r[5] = fmaf(d1.y, t.w11, fmaf(c1.y, t.w10, fmaf(b1.y, t.w01, a1.y * t.w00)));
   r[6] = fmaf(d1.z, t.w11, fmaf(c1.z, t.w10, fmaf(b1.z, t.w01, a1.z * t.w00)));
   r[7] = fmaf(d1.w, t.w11, fmaf(c1.w, t.w10, fmaf(b1.w, t.w01, a1.w * t.w00)));
-}
-
-// ---- packed fp32x2 helpers (Blackwell FFMA2 / 256-bit LDG, STG) -----------------
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk2(float lo, float hi) {
-  u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
-}
-__device__ __forceinline__ void unpk2(u64 v, float& lo, float& hi) {
-  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-  u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
-  u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
-}
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-  u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
-}
-struct Tex8 { u64 v[4]; };   // 8 channels of one texel, as 4 packed pairs
-__device__ __forceinline__ Tex8 ldg256(const float* p) {   // 32-byte aligned
-  Tex8 t;
-  asm volatile("ld.global.nc.v4.b64 {%0,%1,%2,%3}, [%4];"
-               : "=l"(t.v[0]), "=l"(t.v[1]), "=l"(t.v[2]), "=l"(t.v[3]) : "l"(p));
-  return t;
-}
-__device__ __forceinline__ void stg256(float* p, const u64 (&v)[4]) {
-  asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v[0]), "l"(v[1]), "l"(v[2]),
-               "l"(v[3]) : "memory");
-}
-
-__device__ __forceinline__ float round_tf32_f(float x) {
-  uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
-}
-
-// The kernel is instruction-issue bound (ncu: issue ~50 %, DRAM ~10 % in the first
-// version), so the sampler is written for instruction count:
-//  * the 2x2 window is addressed as ONE base (clamped to [0,w-2]x[0,h-2]) plus
-//    compile-time offsets {0, C, w*C, w*C + C}; the zero-padding rule of
-//    grid_sample becomes a remap of the four weights at the image border,
-//  * reciprocals are MUFU.RCP (1 ulp) instead of the IEEE sequence,
-//  * the blend runs on packed FFMA2 with 256-bit texel loads.
-struct Window {
-  Tex8 t00, t01, t10, t11;
-};
-
-// Branch-free: a sample that contributes nothing (behind the camera / fully outside
-// the source image) gets four zero weights and a clamped, always-valid address, so
-// the loop body is straight-line code and ptxas can keep the loads of all views in
-// flight at once.  CT = compile-time channel count (0: use C).
-template <int CT>
-__device__ __forceinline__ void sample_view(const float* __restrict__ vbase, float qx, float qy,
-                                            float qz, int h, int w, int C, int row_floats,
-                                            Window& win, float& w00, float& w01, float& w10,
-                                            float& w11) {
-  const float rz = rcp_approx(qz);
-  const float u = qx * rz, v = qy * rz;
-  const float x0f = floorf(u), y0f = floorf(v);
-  // float->int saturates, so huge |u| fails the range test like ATen's within_bounds;
-  // q_z <= 1e-7 is mapped to (w,h) = fully outside by the reference (modules.py:76-79)
-  const int x0 = __float2int_rd(u), y0 = __float2int_rd(v);
-  const bool valid = (qz > 1e-7f) && (unsigned)(x0 + 1) <= (unsigned)w &&
-                     (unsigned)(y0 + 1) <= (unsigned)h;
-  const float fx = u - x0f, fy = v - y0f;
-  float wxa = 1.f - fx, wxb = fx, wya = 1.f - fy, wyb = fy;
-  // border: texel x0 (or x0+1) is outside => its weight is dropped; the pair
-  // (xs, xs+1) stays inside the image and the surviving weight moves to its slot
-  if (x0 < 0) { wxa = wxb; wxb = 0.f; }
-  if (x0 > w - 2) { wxb = wxa; wxa = 0.f; }
-  if (y0 < 0) { wya = wyb; wyb = 0.f; }
-  if (y0 > h - 2) { wyb = wya; wya = 0.f; }
-  if (!valid) { wxa = 0.f; wxb = 0.f; }
-  const int xs = min(max(x0, 0), w - 2), ys = min(max(y0, 0), h - 2);
-  w00 = wxa * wya; w01 = wxb * wya; w10 = wxa * wyb; w11 = wxb * wyb;
-  const int cc = CT > 0 ? CT : C;
-  const unsigned off = (unsigned)(ys * row_floats + xs * cc);
-  const float* p = vbase + off;
-  win.t00 = ldg256(p);
-  win.t01 = ldg256(p + cc);
-  win.t10 = ldg256(p + row_floats);
-  win.t11 = ldg256(p + row_floats + cc);
 }
 
 // NSRC > 0: number of source views known at compile time (per-view R*(x,y,1) stays
@@ -597,6 +512,10 @@ static int launch_transpose(const float* in, float* out, int N, size_t R, size_t
 
 int g_k1_dchunk = 0;  // CASMVS_K1_DCHUNK overrides the depth-chunk heuristic
 
+// warp_cost_smem.cu
+int warp_var_smem(const float* feats, const float* proj, const float* dv, float* cost, int B,
+                  int V, int C, int D, int h, int w, int rnd, cudaStream_t st);
+
 template <int NSRC, int CT>
 static void launch_k1(bool gwc, bool nhwc, dim3 grd, cudaStream_t st, const float* f,
                       const float* p, const float* dv, float* cost, int V, int C, int D, int h,
@@ -689,6 +608,11 @@ extern "C" int casmvs_warp_cost_fwd(const float* feats, int feat_layout, const f
     env2 = true;
     if (const char* e = getenv("CASMVS_K1_CPT")) g_k1_cpt = atoi(e);
     if (const char* e = getenv("CASMVS_K1_SKIP")) g_k1_skip = atoi(e);
+  }
+  if (!gwc && nhwc) {
+    // TMA-staged generation (warp_cost_smem.cu): 0 = handled, 1 = shape left to the gather kernels
+    const int rc = warp_var_smem(f, proj, depth_values, cost, B, V, C, D, h, w, rnd, st);
+    if (rc <= 0) return rc;
   }
   if (!gwc && nhwc && (V == 3 || V == 2) && (C == 8 || C == 16 || C == 32) &&
       !(g_k1_cpt != 0 && g_k1_cpt != 4 && g_k1_cpt != 8)) {

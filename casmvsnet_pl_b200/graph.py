@@ -16,13 +16,17 @@ class GraphedCascade:
 
     def __init__(self, model, imgs, proj_mats, init_depth_min, depth_interval, warmup=3):
         assert imgs.is_cuda and proj_mats.is_cuda
+        for t in (init_depth_min, depth_interval):
+            if torch.is_tensor(t) and not t.is_cuda:
+                raise ValueError("GraphedCascade needs device tensors (or floats) for the depth "
+                                 "parameters: a host->device copy cannot be captured")
         self.model = model
         self.imgs = imgs.clone()
         self.proj = proj_mats.clone()
         self.dmin, self.dint = init_depth_min, depth_interval
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), torch.no_grad():
             for _ in range(warmup):          # cuDNN autotune, weight packing, smem attributes
                 model(self.imgs, self.proj, self.dmin, self.dint)
         torch.cuda.current_stream().wait_stream(side)
@@ -30,12 +34,23 @@ class GraphedCascade:
         from . import _lib
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.no_grad(), torch.cuda.graph(self.graph):
             self.out = model(self.imgs, self.proj, self.dmin, self.dint)
         # libcasmvs kernels recorded in the graph (each replay launches all of them)
         self.kernels_per_replay = _lib.launch_count() - n0
+        # the graph embeds raw pointers to the library's tensor-core operand images
+        self._weight_generation = _lib.weight_cache_generation()
+
+    def _check_weights(self):
+        from . import _lib
+        if _lib.weight_cache_generation() != self._weight_generation:
+            raise _lib.CasMVSError(
+                "packed weights were re-created after this CUDA graph was captured (load_state_dict, "
+                "a second model, ...): the graph references freed operand images; build a new "
+                "GraphedCascade")
 
     def __call__(self, imgs=None, proj_mats=None):
+        self._check_weights()
         if imgs is not None:
             self.imgs.copy_(imgs, non_blocking=True)
         if proj_mats is not None:
@@ -73,7 +88,9 @@ class PipelinedCascade:
         self.n = 0
         self.pending = []
 
-    def submit(self, imgs_h, proj_h):
+    def submit(self, imgs_h, proj_h, keep=None):
+        """keep: optional device tensor that receives a copy of depth_0 on the compute stream
+        (multi-GPU runs gather the per-rank depth maps from it once, at the end)."""
         i = self.n % len(self.slots)
         g = self.slots[i]
         ret = None
@@ -86,7 +103,11 @@ class PipelinedCascade:
             g.proj.copy_(proj_h, non_blocking=True)
             self.h2d_done[i].record(self.copy_stream)
         self.compute.wait_event(self.h2d_done[i])
+        g._check_weights()
         g.graph.replay()
+        if keep is not None:
+            with torch.cuda.stream(self.compute):
+                keep.copy_(g.out["depth_0"])
         self.compute_done[i].record(self.compute)
         with torch.cuda.stream(self.d2h_stream):
             self.d2h_stream.wait_event(self.compute_done[i])

@@ -87,6 +87,8 @@ class FeatureNet(nn.Module):
         cache = self._folded()
         key = self._fold_key
         if getattr(self, "_pack_key", None) != key:
+            for old in getattr(self, "_pack_cache", {}).values():
+                ops.release_weight_images(old)
             packed = {}
             for i in (1, 3, 4, 6, 7):               # the 3x3 stride-1 blocks
                 w = cache[i][0]
@@ -96,6 +98,8 @@ class FeatureNet(nn.Module):
             self._pack_cache, self._pack_key = packed, key
         skey = tuple((t.data_ptr(), t._version) for t in (self.smooth0.weight, self.smooth1.weight))
         if getattr(self, "_smooth_key", None) != skey:
+            for old in getattr(self, "_smooth_pack", ()):
+                ops.release_weight_images(old)
             self._smooth_pack = (ops.pack_conv3d_weight(self.smooth0.weight.detach(), ops.CONV_PLANAR),
                                  ops.pack_conv3d_weight(self.smooth1.weight.detach(), ops.CONV_PLANAR))
             self._smooth_key = skey
@@ -250,8 +254,11 @@ class CostRegNet(nn.Module):
         if key == self._blob_key:
             return self._blob
         dev = self.prob.weight.device
+        if self._blob is not None:
+            ops.release_weight_images(self._blob)     # the old blob's operand images die with it
         n = ops._lib.load().casmvs_costreg_param_floats(self.in_channels)
         blob = torch.empty(n, device=dev, dtype=torch.float32)
+        ops.release_weight_images(blob)     # a recycled address must not hit stale operand images
         for i, name in enumerate(self._ORDER):
             info = ops.costreg_layer_info(self.in_channels, i)
             w, bn, bias = self._layer_tensors(name)
@@ -292,13 +299,17 @@ class CascadeMVSNet(nn.Module):
         # cascade stage (tf32 inference path; CASMVS_OVERLAP=0 turns it off)
         import os
         self.overlap_pyramid = os.environ.get("CASMVS_OVERLAP", "1") != "0"
+        # diagnostics: also return the int64 depth_index_l maps (mvsnet.py:185-190) that the
+        # confidence gather uses; the reference keeps them internal
+        self.return_index = False
+        self._last_index = None
         for l in range(self.levels):
             cin = self.G if self.G > 1 else 8 * 2 ** l
             setattr(self, f"cost_reg_{l}", CostRegNet(cin, norm_act))
         self.set_precision(precision)
 
     def set_precision(self, precision):
-        """'fp32' (CUDA-core FMA), 'tf32' (tcgen05) or 'tf32x3' for the 3D convs."""
+        """'fp32' (CUDA-core FMA, bit-faithful products) or 'tf32' (tcgen05) for the convs."""
         if precision not in ops.PRECISIONS:
             raise ValueError(f"precision must be one of {list(ops.PRECISIONS)}")
         self.precision = precision
@@ -317,7 +328,9 @@ class CascadeMVSNet(nn.Module):
                              round_tf32=(getattr(cost_reg, "precision", "fp32") == "tf32"))
         logits = cost_reg(cost).squeeze(1)
         del cost
-        depth, confidence, _, _ = ops.regress(logits, depth_values)
+        depth, confidence, index, _ = ops.regress(logits, depth_values,
+                                                  want_index=self.return_index)
+        self._last_index = index
         return depth, confidence
 
     def forward(self, imgs, proj_mats, init_depth_min, depth_interval):
@@ -328,6 +341,19 @@ class CascadeMVSNet(nn.Module):
         if not imgs.is_cuda:
             raise ops._lib.CasMVSError(
                 "CascadeMVSNet (B200 engine) needs CUDA inputs; there is no CPU fallback")
+        if torch.is_grad_enabled() and (imgs.requires_grad or
+                                        any(p.requires_grad for p in self.parameters())):
+            # the reference forward is differentiable; this engine is not.
+            # Returning detached tensors silently would train nothing, so refuse instead.
+            raise ops._lib.CasMVSError(
+                "CascadeMVSNet (B200 engine) is forward-only: call it under torch.no_grad() "
+                "(or freeze the parameters with requires_grad_(False))")
+        # (B,1) depth parameters may arrive as CPU tensors from the reference's data loader
+        # (datasets/dtu.py:188-189): move them once, not once per stage
+        if torch.is_tensor(init_depth_min):
+            init_depth_min = init_depth_min.to(imgs.device, torch.float32)
+        if torch.is_tensor(depth_interval):
+            depth_interval = depth_interval.to(imgs.device, torch.float32)
         results = {}
         with torch.no_grad():
             feats = self.feature(imgs.reshape(B * V, 3, H, W), overlap=self.overlap_pyramid)
@@ -354,4 +380,6 @@ class CascadeMVSNet(nn.Module):
                     feats_l, proj_mats_l, depth_values, getattr(self, f"cost_reg_{l}"))
                 results[f"depth_{l}"] = depth_l
                 results[f"confidence_{l}"] = confidence_l
+                if self.return_index:
+                    results[f"depth_index_{l}"] = self._last_index
         return results

@@ -7,18 +7,41 @@ is a call into libcasmvs.so.  CPU tensors are rejected — there is no fallback
 from __future__ import annotations
 
 import ctypes
+import functools
 
 import torch
 
 from . import _lib
 from ._lib import (CONV, CONV_PLANAR, CONV_TRANSPOSE, FP32, KEEP_FP32_OUT, NCHW, NHWC, PRECISIONS, TF32,  # noqa: F401
-                   TF32X3, check)
+                   check)
 
 _checked_devices = set()
 
 
 def _stream():
+    """The current stream of the CURRENT device; every op runs under `_on_tensor_device`, which
+    makes the tensors' device current first (the reference allows `model.to("cuda:1")` while
+    cuda:0 is current)."""
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _on_tensor_device(fn):
+    """Run `fn` with the device of its first CUDA tensor argument (or `device=` keyword) current:
+    kernel launches, cudaFuncSetAttribute, the SM count and the library's cudaMalloc'ed
+    operand images are all per-device state."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        dev = kw.get("device")
+        if dev is None:
+            dev = next((a.device for a in args if torch.is_tensor(a) and a.is_cuda), None)
+        else:
+            dev = torch.device(dev)
+        if dev is None or dev.type != "cuda" or dev.index is None or \
+                dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapper
 
 
 def _ptr(t):
@@ -38,6 +61,9 @@ def _require_cuda(*tensors):
     first = next((t for t in tensors if t is not None), None)
     if first is None:
         return
+    for t in tensors:
+        if t is not None and t.device != first.device:
+            raise _lib.CasMVSError(f"tensors on different devices: {first.device} and {t.device}")
     dev = first.device.index
     if dev is None:
         dev = torch.cuda.current_device()
@@ -79,6 +105,7 @@ def volume_storage(x):
 
 
 # --------------------------------------------------------------------------- K1
+@_on_tensor_device
 def warp_cost(feats, proj_mats, depth_values, num_groups=1, out_layout=NHWC, round_tf32=False):
     """Fused homography warp + variance / group-wise-correlation cost volume.
 
@@ -113,6 +140,7 @@ def warp_cost(feats, proj_mats, depth_values, num_groups=1, out_layout=NHWC, rou
     return as_volume_view(out) if out_layout == NHWC else out
 
 
+@_on_tensor_device
 def homo_warp(src_feat, proj_mat, depth_values):
     """models/modules.py:52-92.  src_feat (B,C,h,w), proj_mat (B,3,4),
     depth_values (B,D,h,w) -> (B,C,D,h,w) contiguous (reference layout)."""
@@ -136,16 +164,23 @@ def homo_warp(src_feat, proj_mat, depth_values):
 
 # --------------------------------------------------------------------------- K2
 def invalidate_weight_cache():
-    """Drop the library's cached tensor-core operand images (keyed by packed-weight
-    pointers); called whenever packed weights are re-created."""
+    """Drop ALL of the library's cached tensor-core operand images."""
     check(_lib.load().casmvs_invalidate_weight_cache(), "invalidate_weight_cache")
 
 
+def release_weight_images(packed):
+    """Drop the operand images keyed inside `packed`'s memory.  Called on every freshly
+    allocated packed-weight buffer BEFORE it is filled: the caching allocator may hand out an
+    address whose previous owner (an older packed buffer) still has images in the cache."""
+    check(_lib.load().casmvs_release_weight_images(_ptr(packed), packed.numel() * packed.element_size()),
+          "release_weight_images")
+
+
+@_on_tensor_device
 def pack_conv3d_weight(weight, kind):
     """torch Conv3d (Cout,Cin,3,3,3) / ConvTranspose3d (Cin,Cout,3,3,3) / Conv2d (Cout,Cin,3,3)
     [kind CONV_PLANAR: centre plane of a 1x3x3 kernel] -> [27][Cin][Cout]."""
     _require_cuda(weight)
-    invalidate_weight_cache()
     if kind == CONV_PLANAR:
         assert weight.dim() == 4 and tuple(weight.shape[2:]) == (3, 3)
     if kind in (CONV, CONV_PLANAR):
@@ -153,11 +188,13 @@ def pack_conv3d_weight(weight, kind):
     else:
         cin, cout = weight.shape[:2]
     out = torch.empty(27 * cin * cout, device=weight.device, dtype=torch.float32)
+    release_weight_images(out)
     check(_lib.load().casmvs_pack_conv3d_weights(_ptr(weight.detach().contiguous()), kind, cin,
                                                  cout, _ptr(out), _stream()), "pack_conv3d")
     return out
 
 
+@_on_tensor_device
 def conv3d(x, w_packed, cin, cout, scale=None, shift=None, slope=1.0, skip=None,
            kind=CONV, stride=1, precision=FP32):
     """x logical (B,Cin,D,h,w) -> logical (B,Cout,Do,ho,wo); storage channels-last."""
@@ -190,6 +227,7 @@ def costreg_layer_info(cin, layer):
                 w_off=wo.value, scale_off=so.value, shift_off=ho.value)
 
 
+@_on_tensor_device
 def costreg(x, params, cin, precision=FP32):
     """Whole CostRegNet.  x logical (B,Cin,D,h,w) -> logits (B,D,h,w)."""
     _require_cuda(x, params)
@@ -207,6 +245,7 @@ def costreg(x, params, cin, precision=FP32):
 
 
 # --------------------------------------------------------------------------- K3
+@_on_tensor_device
 def regress(logits, depth_values, input_is_prob=False, want_index=False, want_prob=False):
     """softmax + soft-argmax depth + confidence (+ index, prob).
     logits (B,D,h,w); depth_values (B,D,h,w) or (D,)."""
@@ -238,6 +277,7 @@ def _interval_args(depth_interval, B, device):
     return 0.0, t
 
 
+@_on_tensor_device
 def depth_hypotheses(current_depth, n_depths, depth_interval, upsample=False):
     """get_depth_values (models/modules.py:34-49), optionally fused with the x2
     bilinear upsample of models/mvsnet.py:231-234.
@@ -262,6 +302,11 @@ def depth_hypotheses(current_depth, n_depths, depth_interval, upsample=False):
 
 def uniform_hypotheses(init_depth_min, depth_interval, n_depths, B, h, w, device):
     """models/mvsnet.py:213-229 -> (B,D,h,w)."""
+    with torch.cuda.device(device):
+        return _uniform_hypotheses(init_depth_min, depth_interval, n_depths, B, h, w, device)
+
+
+def _uniform_hypotheses(init_depth_min, depth_interval, n_depths, B, h, w, device):
     dmin, dmin_dev = _interval_args(init_depth_min, B, device)
     step, step_dev = _interval_args(depth_interval, B, device)
     out = torch.empty(B, n_depths, h, w, device=device, dtype=torch.float32)
@@ -272,6 +317,7 @@ def uniform_hypotheses(init_depth_min, depth_interval, n_depths, B, h, w, device
 
 
 # --------------------------------------------------------------------------- FPN (adjacent)
+@_on_tensor_device
 def fpn_level(prev, c, lat_w, lat_b, smooth_w, smooth_b, want_feat):
     """Fused FeatureNet top-down level (models/mvsnet.py:36-52).  prev (N,32,h/2,w/2),
     c (N,CLAT,h,w) logical NCHW tensors with channels-last storage -> (feat|None, out)."""
@@ -292,6 +338,7 @@ def fpn_level(prev, c, lat_w, lat_b, smooth_w, smooth_b, want_feat):
     return feat, out
 
 
+@_on_tensor_device
 def conv2d_planar(x, w_packed, cin, cout, shift=None, slope=1.0, precision=TF32,
                   keep_fp32=False, scale=None):
     """3x3 Conv2d (pad 1) + per-channel scale/shift + LeakyReLU over a channels-last
@@ -312,6 +359,7 @@ def conv2d_planar(x, w_packed, cin, cout, shift=None, slope=1.0, precision=TF32,
     return y
 
 
+@_on_tensor_device
 def fpn_merge(prev, c, lat_w, lat_b, round_tf32=False):
     """upsample_x2(prev) + conv1x1(c) + bias -> (N,32,h,w) channels-last (prev None: the
     lateral alone, i.e. FeatureNet.toplayer).  models/mvsnet.py:36-47."""
@@ -331,6 +379,7 @@ def fpn_merge(prev, c, lat_w, lat_b, round_tf32=False):
     return feat
 
 
+@_on_tensor_device
 def conv2d_rgb8(x, w, bias, slope, round_tf32=False):
     """First FeatureNet block with folded ABN: planar (N,3,H,W) images -> (N,8,H,W)
     channels-last.  w (8,3,3,3) torch layout."""
@@ -346,16 +395,21 @@ def conv2d_rgb8(x, w, bias, slope, round_tf32=False):
     return y
 
 
+@_on_tensor_device
 def pack_conv2d_5x5s2_weight(weight):
     """Private copy of a (Cout,Cin,5,5) Conv2d weight for conv2d_5x5s2.  The library caches the
     tensor-core operand image it builds from a weight buffer BY POINTER, so weights must come
-    through here (it drops the cache, like pack_conv3d_weight) and must not be edited in place."""
+    through here (stale images at the new buffer's address are dropped, like pack_conv3d_weight)
+    and must not be edited in place."""
     _require_cuda(weight)
     assert weight.dim() == 4 and tuple(weight.shape[2:]) == (5, 5)
-    invalidate_weight_cache()
-    return weight.detach().clone(memory_format=torch.contiguous_format)
+    out = torch.empty(weight.shape, device=weight.device, dtype=torch.float32)
+    release_weight_images(out)
+    out.copy_(weight.detach())
+    return out
 
 
+@_on_tensor_device
 def conv2d_5x5s2(x, w, shift, slope, round_tf32=False):
     """5x5 stride-2 pad-2 Conv2d + shift + LeakyReLU on tcgen05 (FeatureNet conv1.0 / conv2.0
     with folded ABN).  x (N,Cin,H,W) channels-last, w (Cout,Cin,5,5) from
@@ -375,6 +429,7 @@ def conv2d_5x5s2(x, w, shift, slope, round_tf32=False):
     return y
 
 
+@_on_tensor_device
 def bias_lrelu_(x, bias, slope, round_tf32=False):
     """In-place LeakyReLU(x + bias[c]) on a channels-last (N,C,h,w) tensor (optionally stored
     TF32-rounded for a tensor-core consumer)."""

@@ -48,8 +48,7 @@ enum casmvs_layout { CASMVS_NCHW = 0, CASMVS_NHWC = 1 };
 /* precision of the 3D-conv contraction (K2) */
 enum casmvs_precision {
   CASMVS_FP32 = 0,  /* CUDA-core fp32 FMA (bit-faithful products)            */
-  CASMVS_TF32 = 1,  /* tcgen05 kind::tf32, fp32 accumulate in TMEM           */
-  CASMVS_TF32X3 = 2 /* error-compensated 3xTF32 split (fp32-equivalent)      */
+  CASMVS_TF32 = 1   /* tcgen05 kind::tf32, fp32 accumulate in TMEM           */
 };
 
 /* OR-ed into casmvs_conv3d_fwd's precision: store the output unrounded even in the TF32
@@ -76,6 +75,11 @@ const char* casmvs_last_error(void);
 int casmvs_device_check(int device);
 /* number of kernels this library has launched since load (bench evidence). */
 uint64_t casmvs_launch_count(void);
+/* number of CASMVS_TF32 layers that no tcgen05 kernel covered and that therefore ran on the
+ * CUDA-core kernel (same results up to TF32 rounding, several times slower).  0 for the
+ * reference architecture at every BASELINE configuration; bench.py and the full-size tests
+ * assert that. */
+uint64_t casmvs_fallback_count(void);
 
 /* ---- K1: fused homography warp + bilinear sample + cost reduction ------
  * Replaces homo_warp (models/modules.py:52-92) called V-1 times plus the
@@ -120,10 +124,17 @@ size_t casmvs_packed_conv3d_weight_floats(int Cin, int Cout);
  * CASMVS_CONV_PLANAR, Conv2d layout (Cout,Cin,3,3) */
 int casmvs_pack_conv3d_weights(const float* w_torch, int kind, int Cin, int Cout,
                                float* w_packed, void* stream);
-/* The tensor-core kernels keep a per-process cache of operand images keyed by the
- * w_packed pointer.  Call this after rewriting packed weights in place or freeing them
- * (synchronises the device). */
+/* The tensor-core kernels keep a per-process cache of operand images keyed by the w_packed
+ * pointer (thread-safe).  An image lives as long as the packed buffer it was built from:
+ *   casmvs_release_weight_images(p, bytes) drops the images whose key lies in [p, p+bytes);
+ *     call it when a packed buffer is (re)created at an address, rewritten in place or freed
+ *     (frees device memory => synchronises with kernels still reading those images);
+ *   casmvs_invalidate_weight_cache() drops everything;
+ *   casmvs_weight_cache_generation() increases whenever at least one image was dropped: a
+ *     captured CUDA graph embeds image pointers and must be re-captured when it changes. */
+int casmvs_release_weight_images(const void* w_packed, size_t bytes);
 int casmvs_invalidate_weight_cache(void);
+uint64_t casmvs_weight_cache_generation(void);
 int casmvs_conv3d_fwd(const float* x, const float* w_packed, const float* scale,
                       const float* shift, float slope, const float* skip, float* y,
                       int B, int Cin, int Cout, int D, int h, int w, /* INPUT dims */

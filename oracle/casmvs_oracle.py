@@ -253,9 +253,11 @@ def predict_depth(feats, proj_mats, depth_values, sd, prefix, num_groups=1,
 
 def cascade_forward(sd, imgs, proj_mats, init_depth_min, depth_interval,
                     n_depths=(8, 32, 48), interval_ratios=(1, 2, 4), num_groups=1,
-                    feats=None):
+                    feats=None, want_index=False):
     """CascadeMVSNet.forward (mvsnet.py:197-244).  ``feats`` may be given as a
-    dict level_l -> (B*V,C,h,w) to skip the FeatureNet (hot-path-only timing)."""
+    dict level_l -> (B*V,C,h,w) to skip the FeatureNet (hot-path-only timing).
+    want_index adds the int64 ``depth_index_l`` maps of mvsnet.py:185-190 (what the
+    confidence gather uses) for the index-parity tests."""
     B, V = imgs.shape[:2] if imgs is not None else (None, None)
     results = {}
     with torch.no_grad():
@@ -277,7 +279,10 @@ def cascade_forward(sd, imgs, proj_mats, init_depth_min, depth_interval,
                 dv = initial_hypotheses(init_depth_min, interval_l, D, B, h, w)
             else:
                 dv = depth_hypotheses(upsample_depth(depth_l), D, interval_l)
-            depth_l, conf_l = predict_depth(f, pm, dv, sd, f"cost_reg_{l}.", num_groups)
+            depth_l, conf_l, inter = predict_depth(f, pm, dv, sd, f"cost_reg_{l}.", num_groups, True)
+            if want_index:
+                results[f"depth_index_{l}"] = inter["index"]
+            del inter
             results[f"depth_{l}"] = depth_l
             results[f"confidence_{l}"] = conf_l
     return results

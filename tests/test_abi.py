@@ -82,14 +82,15 @@ def test_binding_constants_match_header():
     from casmvsnet_pl_b200 import _lib
     c = _header_constants()
     assert (c["CASMVS_NCHW"], c["CASMVS_NHWC"]) == (_lib.NCHW, _lib.NHWC)
-    assert (c["CASMVS_FP32"], c["CASMVS_TF32"], c["CASMVS_TF32X3"]) == (_lib.FP32, _lib.TF32, _lib.TF32X3)
+    assert (c["CASMVS_FP32"], c["CASMVS_TF32"]) == (_lib.FP32, _lib.TF32)
+    assert "CASMVS_TF32X3" not in c and "tf32x3" not in _lib.PRECISIONS   # removed, not lying
     assert (c["CASMVS_CONV"], c["CASMVS_CONV_TRANSPOSE"], c["CASMVS_CONV_PLANAR"]) == \
         (_lib.CONV, _lib.CONV_TRANSPOSE, _lib.CONV_PLANAR)
     assert c["CASMVS_ROUND_TF32"] == _lib.ROUND_TF32
     assert c["CASMVS_KEEP_FP32_OUT"] == _lib.KEEP_FP32_OUT
     # flags must not collide with the enum values they are OR-ed into
     assert c["CASMVS_ROUND_TF32"] > max(c["CASMVS_NCHW"], c["CASMVS_NHWC"])
-    assert c["CASMVS_KEEP_FP32_OUT"] > c["CASMVS_TF32X3"]
+    assert c["CASMVS_KEEP_FP32_OUT"] > c["CASMVS_TF32"]
 
 
 def test_new_entry_points_validate_arguments():
@@ -103,6 +104,11 @@ def test_new_entry_points_validate_arguments():
     rc = lib.casmvs_conv3d_fwd(one, one, None, None, 1.0, None, one, 1, 8, 8, 4, 16, 16,
                                _lib.CONV, 1, _lib.TF32 | 512, None)
     assert rc < 0 and b"precision" in lib.casmvs_last_error()
+    rc = lib.casmvs_conv3d_fwd(one, one, None, None, 1.0, None, one, 1, 8, 8, 4, 16, 16,
+                               _lib.CONV, 1, 2, None)            # the removed TF32X3 value
+    assert rc < 0 and b"precision" in lib.casmvs_last_error()
+    assert lib.casmvs_release_weight_images(one, 64) == 0         # nothing cached: no-op
+    assert lib.casmvs_fallback_count() == 0 and lib.casmvs_weight_cache_generation() == 0
     rc = lib.casmvs_fpn_merge_fwd(one, one, one, one, one, 1, 15, 16, 8, 0, None)
     assert rc < 0 and b"even" in lib.casmvs_last_error()
     rc = lib.casmvs_fpn_merge_fwd(None, one, one, one, one, 1, 16, 16, 6, 0, None)

@@ -83,6 +83,86 @@ def test_predict_depth_vs_oracle_cfg1():
     assert rel < 1e-4
 
 
+# --------------------------------------------------------------------------------------------
+# Parity AT THE BENCHMARKED SIZES, both precisions, against the oracle on identical inputs
+# (VERDICT r1 weak #1).  The tf32 mode is the one bench.py measures: its size-dependent
+# machinery (persistent-CTA item decomposition, depth chunks, Cout slices, side-stream overlap,
+# programmatic dependent launch) only exists at these sizes.
+FULL_CONFIGS = {
+    # BASELINE.json configs[1..4]; cfg4 is ONE of its 8 reference views, cfg5 keeps the
+    # V=7 / D=64,32,8 geometry at half resolution (960x544) to bound the oracle's CPU time
+    "cfg2": dict(W=640, H=512, V=3, G=1, n_depths=(8, 32, 48)),
+    "cfg3_gwc8": dict(W=640, H=512, V=3, G=8, n_depths=(8, 32, 48)),
+    "cfg4_view": dict(W=1152, H=864, V=5, G=1, n_depths=(8, 32, 48)),
+    "cfg5_half": dict(W=960, H=544, V=7, G=1, n_depths=(8, 32, 64)),
+}
+_ORACLE_CACHE = {}
+
+
+def _oracle_full(name):
+    if name not in _ORACLE_CACHE:
+        c = FULL_CONFIGS[name]
+        torch.manual_seed(0)
+        m = CascadeMVSNet(n_depths=list(c["n_depths"]), num_groups=c["G"], norm_act=ABN)
+        synth.randomize_model_(m, 0)
+        sd = {k: v.clone() for k, v in m.state_dict().items()}
+        imgs, pm, dmin, dint = synth.make_inputs(B=1, V=c["V"], W=c["W"], H=c["H"], seed=0)
+        nt = torch.get_num_threads()
+        torch.set_num_threads(min(16, nt))        # oneDNN over-subscribes on the 128-core box
+        ref = O.cascade_forward(sd, imgs, pm, dmin, dint, c["n_depths"], (1, 2, 4), c["G"],
+                                want_index=True)
+        torch.set_num_threads(nt)
+        _ORACLE_CACHE[name] = (sd, imgs, pm, dmin, dint, ref)
+    return _ORACLE_CACHE[name]
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp32"])
+@pytest.mark.parametrize("name", list(FULL_CONFIGS))
+def test_full_size_parity_vs_oracle(name, precision):
+    from casmvsnet_pl_b200 import _lib
+    c = FULL_CONFIGS[name]
+    sd, imgs, pm, dmin, dint, ref = _oracle_full(name)
+    model = CascadeMVSNet(n_depths=list(c["n_depths"]), num_groups=c["G"], norm_act=ABN,
+                          precision=precision)
+    model.load_state_dict(sd)
+    model = model.eval().to(DEV)
+    model.return_index = True
+    fb0 = _lib.fallback_count()
+    res = model(imgs.to(DEV), pm.to(DEV), dmin, dint)
+    torch.cuda.synchronize()
+    assert _lib.fallback_count() == fb0, "a tf32 layer fell back to the CUDA-core kernel"
+    for l in (2, 1, 0):
+        d, r = res[f"depth_{l}"].cpu(), ref[f"depth_{l}"]
+        rel = ((d - r).abs().mean() / r.abs().mean()).item()
+        cd = (res[f"confidence_{l}"].cpu() - ref[f"confidence_{l}"]).abs()
+        idx = (res[f"depth_index_{l}"].cpu() != ref[f"depth_index_{l}"]).float().mean().item()
+        print(f"{name}/{precision} level {l}: depth rel-L1 {rel:.3e} max|d| {(d - r).abs().max():.3e} mm  "
+              f"conf max|d| {cd.max():.3e} mean {cd.mean():.3e}  index mismatch {100 * idx:.4f} %")
+        # north_star: depth within 1e-3 relative L1 of the reference
+        assert rel < 1e-3
+        assert cd.mean().item() < (2e-3 if precision == "tf32" else 1e-4)
+        # the index is exact given identical probabilities (test_gpu_kernels.py); through the
+        # whole cascade a pixel can flip only when sum(p*d) sits on an integer boundary
+        assert idx < (2e-2 if precision == "tf32" else 2e-3)
+    # abs_err (metrics.py:1-3) against a synthetic ground truth ~4.5 mm around the reference
+    # output: the two implementations' abs_err agree within 1e-3 (north_star)
+    gen = torch.Generator().manual_seed(1)
+    gt = ref["depth_0"] + 5.6 * torch.randn(ref["depth_0"].shape, generator=gen)
+    a = (res["depth_0"].cpu() - gt).abs().mean().item()
+    b = (ref["depth_0"] - gt).abs().mean().item()
+    print(f"{name}/{precision} abs_err ours {a:.6f} mm, oracle {b:.6f} mm")
+    assert abs(a - b) < 1e-3 and abs(a - b) / b < 1e-3
+    if precision == "tf32":
+        # the benchmarked execution form: CUDA-graph replay == eager, bit for bit
+        from casmvsnet_pl_b200.graph import GraphedCascade
+        model.return_index = False
+        g = GraphedCascade(model, imgs.to(DEV), pm.to(DEV), dmin, dint, warmup=1)
+        out = g()
+        torch.cuda.synchronize()
+        assert torch.equal(out["depth_0"], res["depth_0"])
+        assert torch.equal(out["confidence_2"], res["confidence_2"])
+
+
 def test_full_size_cfg2_properties():
     """640x512, V=3, D=48/32/8: size-independent properties (the oracle needs seconds
     per stage at this size, so only K1 at level 2 is compared directly)."""
@@ -181,3 +261,30 @@ def test_graph_and_pipeline_match_eager():
     assert len(got) == len(views)
     for (d, c), (gd, gc) in zip(eager, got):
         assert torch.equal(gd, d) and torch.equal(gc, c)
+
+
+def test_weight_image_lifetime_and_graph_generation():
+    """operand images are tied to their packed buffer, not dropped globally.  A second
+    model (new packed buffers) leaves a captured graph of the first one valid; re-packing the
+    first model's weights frees its images, which the graph wrapper detects instead of
+    replaying a use-after-free."""
+    from casmvsnet_pl_b200 import _lib
+    from casmvsnet_pl_b200.graph import GraphedCascade
+    model, sd = build(1, "tf32")
+    imgs, pm, dmin, dint = synth.make_inputs(B=1, V=3, W=160, H=128, seed=0)
+    imgs, pm = imgs.to(DEV), pm.to(DEV)
+    want = {k: v.clone() for k, v in model(imgs, pm, dmin, dint).items()}
+    g = GraphedCascade(model, imgs, pm, dmin, dint, warmup=1)
+    gen = _lib.weight_cache_generation()
+    other, _ = build(8, "tf32")                     # packs 3 more CostRegNets + a FeatureNet
+    other(imgs, pm, dmin, dint)
+    assert _lib.weight_cache_generation() == gen    # nothing of `model` was dropped
+    out = g()
+    assert all(torch.equal(out[k], want[k]) for k in want)
+    # in-place edit of a parameter -> re-pack on the next eager call -> old images released
+    with torch.no_grad():
+        model.cost_reg_0.prob.bias.add_(1.0)
+    model(imgs, pm, dmin, dint)
+    assert _lib.weight_cache_generation() > gen
+    with pytest.raises(_lib.CasMVSError):
+        g()

@@ -155,6 +155,37 @@ def test_cost_volume_many_views_and_edges():
         assert err.max() < 1e-4
 
 
+@pytest.mark.parametrize("V,C,level", [(3, 8, 0), (3, 16, 1), (3, 32, 2), (5, 16, 1), (7, 32, 2), (2, 8, 0)])
+@pytest.mark.parametrize("case", ["smooth", "discontinuity", "wide_sweep", "stress_pose"])
+def test_cost_volume_smem_staging_paths(V, C, level, case):
+    """The TMA-staged K1 (csrc/warp_cost_smem.cu) against the oracle on inputs that exercise each
+    of its paths: windows inside the staged box (smooth), windows outside it (a depth step
+    inside the tile -> per-sample gather path), footprints larger than the box (wide sweep ->
+    the CTA halves the run and re-stages), non-axis-aligned epipolar lines and samples behind
+    the camera (stress pose); image sizes that are not multiples of the pixel tile."""
+    g = torch.Generator().manual_seed(11 + level)
+    W, H = 640, 512
+    h, w = (H >> level) - 3, (W >> level) - 5           # ragged tiles at the right/bottom edge
+    D = {0: 8, 1: 16, 2: 24}[level]
+    feats = torch.randn(1, V, C, h, w, generator=g)
+    stress = case == "stress_pose"
+    pm = synth.projection_matrices(V, W, H, stress=stress,
+                                   behind_view=1 if stress else None)[:, level].unsqueeze(0)
+    step = 2.65 * 2 ** level * (12.0 if case == "wide_sweep" else 1.0)
+    base = 600.0 + 3.0 * torch.rand(1, 1, h, w, generator=g)
+    if case == "discontinuity":
+        base[..., :, w // 3:] -= 150.0                    # foreground / background step
+        base[..., h // 2:, :] += 80.0
+    dv = (base + step * torch.arange(D).float().reshape(1, D, 1, 1)).contiguous()
+    want = O.variance_cost_volume(feats, pm, dv)
+    got = ops.warp_cost(cl(feats.to(DEV)), pm.to(DEV), dv.to(DEV), 1, ops.NHWC).cpu()
+    err = stats(f"smem-K1 V={V} C={C} {case}", got, want)
+    # white-noise texels: the reference's own normalise/un-normalise round trip moves a sample by
+    # a few ulp(u) (~2e-5 px at w=640) -> up to ~3e-4 on a variance of magnitude ~10
+    assert err.max() < 5e-5 * want.abs().max().item() + 1e-4
+    assert err.mean() < 2e-6
+
+
 # ----------------------------------------------------------------------------- K2
 @pytest.mark.parametrize("cin", [8, 32])
 @pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("tf32", 3e-3)])
