@@ -67,7 +67,8 @@ class PipelinedCascade:
         pipe = PipelinedCascade(model, imgs_example, proj_example, depth_min, depth_interval)
         for imgs_h, proj_h in views:            # pinned host tensors
             done = pipe.submit(imgs_h, proj_h)  # returns the results of the view submitted
-            ...                                 # `depth` slots earlier (or None while filling)
+            ...                                 # `slots` calls earlier (or None while filling);
+                                                # valid until `slots` further submits
         tail = pipe.drain()
     Results are (depth_0, confidence_2) pinned host tensors, what eval.py:224-226 reads back.
     """
@@ -80,11 +81,16 @@ class PipelinedCascade:
         self.compute = torch.cuda.current_stream()
         self.h2d_done = [torch.cuda.Event() for _ in range(slots)]
         self.compute_done = [torch.cuda.Event() for _ in range(slots)]
-        self.d2h_done = [torch.cuda.Event() for _ in range(slots)]
+        # pinned result buffers: a ring twice as long as the slot ring, so that the tensors a
+        # submit() returns are not the target of any copy enqueued by that same call -- they
+        # stay valid until `slots` further submits
         self.out_h = []
-        for g in self.slots:
-            self.out_h.append((torch.empty(g.out["depth_0"].shape).pin_memory(),
-                               torch.empty(g.out["confidence_2"].shape).pin_memory()))
+        g0 = self.slots[0]
+        for _ in range(2 * slots):
+            self.out_h.append((torch.empty(g0.out["depth_0"].shape).pin_memory(),
+                               torch.empty(g0.out["confidence_2"].shape).pin_memory()))
+        self.d2h_done = [torch.cuda.Event() for _ in range(2 * slots)]
+        self.slot_read = [None] * slots
         self.n = 0
         self.pending = []
 
@@ -103,25 +109,30 @@ class PipelinedCascade:
             g.proj.copy_(proj_h, non_blocking=True)
             self.h2d_done[i].record(self.copy_stream)
         self.compute.wait_event(self.h2d_done[i])
+        if self.slot_read[i] is not None:
+            self.compute.wait_event(self.slot_read[i])
         g._check_weights()
         g.graph.replay()
         if keep is not None:
             with torch.cuda.stream(self.compute):
                 keep.copy_(g.out["depth_0"])
         self.compute_done[i].record(self.compute)
+        j = self.n % len(self.out_h)
         with torch.cuda.stream(self.d2h_stream):
             self.d2h_stream.wait_event(self.compute_done[i])
-            self.out_h[i][0].copy_(g.out["depth_0"], non_blocking=True)
-            self.out_h[i][1].copy_(g.out["confidence_2"], non_blocking=True)
-            self.d2h_done[i].record(self.d2h_stream)
-        self.pending.append(i)
+            self.out_h[j][0].copy_(g.out["depth_0"], non_blocking=True)
+            self.out_h[j][1].copy_(g.out["confidence_2"], non_blocking=True)
+            self.d2h_done[j].record(self.d2h_stream)
+        # the slot's next replay overwrites g.out: it must not start before this D2H has read it
+        self.slot_read[i] = self.d2h_done[j]
+        self.pending.append(j)
         self.n += 1
         return ret
 
     def _collect(self):
-        i = self.pending.pop(0)
-        self.d2h_done[i].synchronize()
-        return self.out_h[i]
+        j = self.pending.pop(0)
+        self.d2h_done[j].synchronize()
+        return self.out_h[j]
 
     def drain(self):
         out = []

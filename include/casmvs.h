@@ -231,6 +231,36 @@ int casmvs_bias_lrelu_nhwc(float* x, const float* bias, float slope, size_t nume
 int casmvs_bias_act_nhwc(float* x, const float* bias, float slope, size_t numel, int C,
                          int round_tf32, void* stream);
 
+/* ---- input pipeline -------------------------------------
+ * T.ToTensor() + T.Normalize(mean, std) of the reference's data sets (datasets/dtu.py:130-137)
+ * for images uploaded as bytes: images (N,H,W,3) uint8 RGB -> out (N,3,H,W) float32,
+ * y = ((float)x / 255 - mean[c]) / std[c] in that operation order (bit-identical to
+ * torchvision).  mean3 / std3 are HOST arrays of 3 floats.  H*W % 4 == 0 when N > 1. */
+int casmvs_normalize_u8_fwd(const uint8_t* images, float* out, int N, int H, int W,
+                            const float* mean3, const float* std3, void* stream);
+
+/* ---- geometric-consistency filter + refinement + back-projection ------
+ * One reference view of eval.py:262-318 on the device; replaces xy_ref2src / xy_src2ref /
+ * check_geo_consistency (eval.py:113-182, numba + cv2.remap on the CPU).  For every reference
+ * pixel and each of the S source views: project with depth_ref, sample the source depth (and
+ * image) bilinearly with cv2.remap's semantics (map rounded to 1/32 px, zero outside), lift
+ * back, mask = |dp| < 1 px and |dd|/d < 1 %.
+ *   depth_ref (H,W); image_ref (H,W,3) or NULL; proba_ref (H/4,W/4) or NULL (= confidence_2,
+ *   upsampled x4 like cv2.resize INTER_LINEAR and compared with conf_thresh);
+ *   depth_src / image_src: HOST arrays of S device pointers; proj_ref2src / proj_src2ref: HOST
+ *   arrays (S,3,4) = (P_src @ inv(P_ref))[:3] / (P_ref @ inv(P_src))[:3]; ref2world (4,4) device.
+ * Outputs (device): depth_refined (H,W) = (depth_ref + sum of consistent reprojections)/(n+1),
+ * image_refined (H,W,3) or NULL, geo_count (H,W) int32, mask_final (H,W) uint8 or NULL
+ * (geo_count >= min_consistent and confidence), points (H,W,3) world coordinates of the
+ * refined depth or NULL; reproj_dbg (S,H,W) / mask_dbg (S,H,W) per-view results or NULL. */
+int casmvs_geo_fuse_fwd(const float* depth_ref, const float* image_ref, const float* proba_ref,
+                        const float* const* depth_src, const float* const* image_src,
+                        const float* proj_ref2src, const float* proj_src2ref,
+                        const float* ref2world, int S, int H, int W, float conf_thresh,
+                        int min_consistent, float* depth_refined, float* image_refined,
+                        int* geo_count, unsigned char* mask_final, float* points,
+                        float* reproj_dbg, unsigned char* mask_dbg, void* stream);
+
 /* ---- layout helpers ------------------------------------------------------ */
 /* (N,C,S) -> (N,S,C) and back, S = product of spatial dims. */
 int casmvs_nchw_to_nhwc(const float* in, float* out, int N, int C, size_t S, void* stream);
