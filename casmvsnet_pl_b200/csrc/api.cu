@@ -117,10 +117,8 @@ extern "C" int casmvs_conv3d_fwd(const float* x, const float* w_packed, const fl
   // the tensor-core layers); the prob head (Cout == 1) feeds the softmax and stays fp32
   const int round_out =
       (precision == CASMVS_TF32 && Cout > 1 && !(flags & CASMVS_KEEP_FP32_OUT)) ? 1 : 0;
-  // a planar (1x3x3) kernel is a 3x3x3 kernel whose outer planes are zero: the CUDA-core
-  // kernel runs it as such
-  return conv3d_direct(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w,
-                       kind == CASMVS_CONV_PLANAR ? CASMVS_CONV : kind, stride, st, round_out);
+  return conv3d_direct(x, w_packed, scale, shift, slope, skip, y, B, Cin, Cout, D, h, w, kind,
+                       stride, st, round_out);
 }
 
 // ---- CostRegNet driver ------------------------------------------------------

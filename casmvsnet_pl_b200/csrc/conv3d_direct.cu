@@ -24,6 +24,7 @@ struct ConvDims {
   int B, Cin, Cout;
   int Di, hi, wi;  // input
   int Do, ho, wo;  // output
+  int kd_lo, kd_hi;  // depth taps to visit: [0,3) for a 3x3x3 kernel, [1,2) for a planar (1x3x3) one
 };
 
 template <int COT>
@@ -73,7 +74,7 @@ conv3d_direct_kernel(const float* __restrict__ x, const float* __restrict__ wpk,
   const float* xb = x + (size_t)b * dm.Di * dm.hi * dm.wi * Cin;
 
   if constexpr (KIND == K_CONV_S1) {
-    for (int kd = 0; kd < 3; ++kd) {
+    for (int kd = dm.kd_lo; kd < dm.kd_hi; ++kd) {
       const int id = od + kd - 1;
       if (id < 0 || id >= dm.Di) continue;
       for (int kh = 0; kh < 3; ++kh) {
@@ -234,6 +235,11 @@ int conv3d_direct(const float* x, const float* wpk, const float* scale, const fl
                   int h, int w, int kind, int stride, cudaStream_t st, int round_out) {
   ConvDims dm;
   dm.B = B; dm.Cin = Cin; dm.Cout = Cout; dm.Di = D; dm.hi = h; dm.wi = w;
+  dm.kd_lo = 0; dm.kd_hi = 3;
+  if (kind == CASMVS_CONV_PLANAR) {      // the two outer weight planes are zero: skip them
+    dm.kd_lo = 1; dm.kd_hi = 2;
+    kind = CASMVS_CONV;
+  }
   if (kind == CASMVS_CONV) {
     dm.Do = (D - 1) / stride + 1; dm.ho = (h - 1) / stride + 1; dm.wo = (w - 1) / stride + 1;
     if (stride == 1) {

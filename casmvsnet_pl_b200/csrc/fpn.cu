@@ -451,3 +451,97 @@ extern "C" int casmvs_conv2d_rgb8_fwd(const float* x, const float* w, const floa
                                                          round_tf32 ? 1 : 0);
   return after_launch("conv2d_rgb8");
 }
+
+// ---- fp32 (CUDA-core) 5x5 stride-2 pad-2 convolution ---------------------------------------
+// The fp32 precision mode of FeatureNet's two strided blocks (ConvBnReLU(8,16,5,2,2) /
+// (16,32,5,2,2), mvsnet.py:16,20): bit-faithful products like every kernel of that mode.
+// CTA = 16 x 8 output pixels x all COUT; the (35 x 19) input footprint is staged in shared
+// memory planar per channel (stride-2 reads of neighbouring threads: 2-way bank conflict at
+// worst), the weights [25][CIN][COUT] are read as warp broadcasts.
+namespace casmvs {
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(128)
+conv2d_5x5s2_fp32_kernel(const float* __restrict__ x, const float* __restrict__ wt,
+                         const float* __restrict__ shift, float slope, float* __restrict__ y,
+                         int H, int W, int Ho, int Wo) {
+  constexpr int TX = 16, TY = 8, IW = 2 * TX + 3, IH = 2 * TY + 3, IWP = IW + 1;
+  extern __shared__ __align__(16) float s_raw[];
+  float* s_in = s_raw;                          // [CIN][IH][IWP]
+  float* s_w = s_raw + CIN * IH * IWP;          // [25][CIN][COUT]
+  const int n = blockIdx.z;
+  const int ox0 = blockIdx.x * TX, oy0 = blockIdx.y * TY;
+  const int ix0 = 2 * ox0 - 2, iy0 = 2 * oy0 - 2;
+  const float* xb = x + (size_t)n * H * W * CIN;
+  for (int i = threadIdx.x; i < IH * IW * CIN; i += blockDim.x) {
+    const int ci = i % CIN, xx = (i / CIN) % IW, yy = i / (CIN * IW);
+    const int gx = ix0 + xx, gy = iy0 + yy;
+    s_in[(ci * IH + yy) * IWP + xx] =
+        (gx >= 0 && gx < W && gy >= 0 && gy < H) ? __ldg(xb + ((size_t)gy * W + gx) * CIN + ci) : 0.f;
+  }
+  for (int i = threadIdx.x; i < 25 * CIN * COUT; i += blockDim.x) {
+    const int co = i % COUT, ci = (i / COUT) % CIN, tap = i / (COUT * CIN);
+    s_w[i] = __ldg(wt + ((size_t)co * CIN + ci) * 25 + tap);      // torch (Cout,Cin,5,5)
+  }
+  __syncthreads();
+  const int lx = threadIdx.x % TX, ly = threadIdx.x / TX;
+  float acc[COUT];
+#pragma unroll
+  for (int k = 0; k < COUT; ++k) acc[k] = 0.f;
+  for (int ky = 0; ky < 5; ++ky)
+    for (int kx = 0; kx < 5; ++kx) {
+      const float* wrow = s_w + (size_t)(ky * 5 + kx) * CIN * COUT;
+#pragma unroll 4
+      for (int ci = 0; ci < CIN; ++ci) {
+        const float a = s_in[(ci * IH + 2 * ly + ky) * IWP + 2 * lx + kx];
+#pragma unroll
+        for (int k = 0; k < COUT; k += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wrow + ci * COUT + k);
+          acc[k] = fmaf(a, w4.x, acc[k]);         acc[k + 1] = fmaf(a, w4.y, acc[k + 1]);
+          acc[k + 2] = fmaf(a, w4.z, acc[k + 2]); acc[k + 3] = fmaf(a, w4.w, acc[k + 3]);
+        }
+      }
+    }
+  const int ox = ox0 + lx, oy = oy0 + ly;
+  if (ox >= Wo || oy >= Ho) return;
+  float* op = y + (((size_t)n * Ho + oy) * Wo + ox) * COUT;
+#pragma unroll
+  for (int k = 0; k < COUT; k += 4) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float t = acc[k + j] + (shift ? __ldg(shift + k + j) : 0.f);
+      v[j] = t >= 0.f ? t : t * slope;
+    }
+    st4(op + k, make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+template <int CIN, int COUT>
+static int launch_5x5_fp32(const float* x, const float* w, const float* shift, float slope, float* y,
+                           int N, int H, int W, cudaStream_t st) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  constexpr int smem = (CIN * 19 * 36 + 25 * CIN * COUT) * 4;
+  auto kfn = conv2d_5x5s2_fp32_kernel<CIN, COUT>;
+  static std::atomic<bool> a[kMaxDevices];
+  if (int rc = opt_in_smem(kfn, smem, a, "conv2d_5x5s2_fp32")) return rc;
+  dim3 grd((Wo + 15) / 16, (Ho + 7) / 8, N);
+  kfn<<<grd, 128, smem, st>>>(x, w, shift, slope, y, H, W, Ho, Wo);
+  return after_launch("conv2d_5x5s2_fp32");
+}
+
+}  // namespace casmvs
+
+extern "C" int casmvs_conv2d_5x5s2_fp32_fwd(const float* x, const float* w, const float* shift,
+                                            float slope, float* y, int N, int Cin, int Cout,
+                                            int H, int W, void* stream) {
+  CASMVS_REQUIRE(x && w && y, "conv2d_5x5s2_fp32: null pointer");
+  CASMVS_REQUIRE(N >= 0 && N <= 65535 && H >= 1 && W >= 1, "conv2d_5x5s2_fp32: bad dims");
+  if (N == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  if (Cin == 8 && Cout == 16) return casmvs::launch_5x5_fp32<8, 16>(x, w, shift, slope, y, N, H, W, st);
+  if (Cin == 16 && Cout == 32) return casmvs::launch_5x5_fp32<16, 32>(x, w, shift, slope, y, N, H, W, st);
+  set_error("conv2d_5x5s2_fp32: only the FeatureNet shapes 8->16 and 16->32 are built (got %d->%d)",
+            Cin, Cout);
+  return -1;
+}

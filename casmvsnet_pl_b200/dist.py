@@ -46,6 +46,8 @@ def sharded_depth_inference(engine, imgs, proj_mats, init_depth_min, depth_inter
     else:
         local = None
     if world == 1:
+        if local is None:                      # empty batch: nothing to infer, nothing to gather
+            return {k: torch.zeros(0, 0, 0, dtype=torch.float32, device=imgs.device) for k in keys}
         return {k: local[k] for k in keys}
 
     # every rank must know the output shapes even if its shard is empty
@@ -61,11 +63,14 @@ def sharded_depth_inference(engine, imgs, proj_mats, init_depth_min, depth_inter
         send = torch.zeros(cap, h, w, dtype=torch.float32, device=imgs.device)
         if local is not None:
             send[: hi - lo] = local[k]
-        recv = [torch.empty_like(send) for _ in range(world)]
-        dist.all_gather(recv, send, group=group)          # the path's single collective
-        parts = []
-        for r in range(world):
-            rlo, rhi = shard_bounds(B, r, world)
-            parts.append(recv[r][: rhi - rlo])
-        out[k] = torch.cat(parts, 0)
+        recv = torch.empty(world * cap, h, w, dtype=torch.float32, device=imgs.device)
+        dist.all_gather_into_tensor(recv, send, group=group)   # the path's single collective
+        if B == world * cap:                   # balanced shards: the gathered tensor IS the result
+            out[k] = recv
+        else:
+            parts = []
+            for r in range(world):
+                rlo, rhi = shard_bounds(B, r, world)
+                parts.append(recv[r * cap: r * cap + rhi - rlo])
+            out[k] = torch.cat(parts, 0)
     return out

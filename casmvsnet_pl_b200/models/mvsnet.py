@@ -17,7 +17,9 @@ from .modules import ConvBnReLU, ConvBnReLU3D, InPlaceABN
 
 
 class FeatureNet(nn.Module):
-    """3-level FPN (reference models/mvsnet.py:7-57).  PyTorch/cuDNN."""
+    """3-level FPN (reference models/mvsnet.py:7-57).  Inference on the GPU runs entirely on this
+    library's kernels in both precision modes (tf32: tcgen05 planar / 5x5 convs; fp32: CUDA-core
+    FMA kernels); PyTorch modules are only the parameter holders and the training / CPU path."""
 
     def __init__(self, norm_act=InPlaceABN):
         super().__init__()
@@ -157,24 +159,50 @@ class FeatureNet(nn.Module):
         return {"level_0": l0, "level_1": l1, "level_2": f2, "_ready": {1: ev1, 0: ev0}}
 
     def _forward_folded(self, x):
-        x = x.contiguous(memory_format=torch.channels_last)
+        """fp32 inference path.  On the GPU every layer runs on this library's CUDA-core fp32
+        kernels (bit-faithful products, no cuDNN / cuBLAS kernel anywhere): first block
+        straight from the planar image batch, 3x3 blocks as planar convolutions over the
+        (views, H, W) volume, 5x5 stride-2 blocks, then the fused top-down levels."""
         cache = self._folded()
+        if not x.is_cuda:                     # CPU: plain torch (never on the product's hot path)
+            x = x.contiguous(memory_format=torch.channels_last)
 
-        def run(t, lo, hi):
-            for w, b, stride, pad, slope in cache[lo:hi]:
-                if t.is_cuda:
-                    # cuDNN conv, then ONE fused bias + LeakyReLU pass (csrc/fpn.cu)
-                    t = F.conv2d(t, w, None, stride, pad)
-                    if not t.is_contiguous(memory_format=torch.channels_last):
-                        t = t.contiguous(memory_format=torch.channels_last)
-                    t = ops.bias_lrelu_(t, b, slope)
-                else:
+            def run(t, lo, hi):
+                for w, b, stride, pad, slope in cache[lo:hi]:
                     t = F.leaky_relu_(F.conv2d(t, w, b, stride, pad), slope)
-            return t
-        c0 = run(x, 0, 2)
-        c1 = run(c0, 2, 5)
-        c2 = run(c1, 5, 8)
+                return t
+            c0 = run(x, 0, 2)
+            c1 = run(c0, 2, 5)
+            c2 = run(c1, 5, 8)
+            return self._head(c0, c1, c2)
+        packed = self._packed_fp32()
+
+        def planar(t, i):
+            w, b, _, _, slope = cache[i]
+            return ops.conv2d_planar(t, packed[i], w.shape[1], w.shape[0], b, slope, ops.FP32)
+
+        def strided(t, i):
+            _, b, _, _, slope = cache[i]
+            return ops.conv2d_5x5s2_fp32(t, packed[i], b, slope)
+
+        w0, b0, _, _, slope0 = cache[0]
+        c0 = planar(ops.conv2d_rgb8(x, w0, b0, slope0), 1)
+        c1 = planar(planar(strided(c0, 2), 3), 4)
+        c2 = planar(planar(strided(c1, 5), 6), 7)
         return self._head(c0, c1, c2)
+
+    def _packed_fp32(self):
+        """Packed weights of the fp32 path ([27][Cin][Cout] planar 3x3 blocks, plain contiguous
+        (O,I,5,5) copies of the strided ones); no tensor-core operand image is involved."""
+        key = self._fold_key
+        if getattr(self, "_pack32_key", None) != key:
+            cache = self._fold_cache
+            packed = {i: ops.pack_conv3d_weight(cache[i][0].contiguous(), ops.CONV_PLANAR)
+                      for i in (1, 3, 4, 6, 7)}
+            for i in (2, 5):
+                packed[i] = cache[i][0].detach().contiguous(memory_format=torch.contiguous_format).clone()
+            self._pack32_cache, self._pack32_key = packed, key
+        return self._pack32_cache
 
     def _forward_modules(self, x):
         # channels-last end to end: level_l come out physically (N,h,w,C)
@@ -185,7 +213,10 @@ class FeatureNet(nn.Module):
         return self._head(c0, c1, c2)
 
     def _head(self, c0, c1, c2):
-        f2 = self.toplayer(c2)
+        if c0.is_cuda and not (self.training or torch.is_grad_enabled()):
+            f2 = ops.fpn_merge(None, c2, self.toplayer.weight, self.toplayer.bias)   # 1x1 lateral
+        else:
+            f2 = self.toplayer(c2)
         if c0.is_cuda and not (self.training or torch.is_grad_enabled()):
             # fused top-down path: upsample + lateral 1x1 + add + 3x3 smooth in one kernel per
             # level (csrc/fpn.cu); the 32-channel full-resolution tensor is never stored

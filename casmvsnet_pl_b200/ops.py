@@ -430,6 +430,24 @@ def conv2d_5x5s2(x, w, shift, slope, round_tf32=False):
 
 
 @_on_tensor_device
+def conv2d_5x5s2_fp32(x, w, shift, slope):
+    """fp32-mode twin of conv2d_5x5s2 (CUDA-core FMA): x (N,Cin,H,W) channels-last,
+    w (Cout,Cin,5,5) contiguous -> (N,Cout,H/2,W/2) channels-last."""
+    _require_cuda(x, w, shift)
+    _no_grad_only(x)
+    xs = x.contiguous(memory_format=torch.channels_last)
+    N, cin, H, W = xs.shape
+    cout = w.shape[0]
+    assert tuple(w.shape) == (cout, cin, 5, 5) and w.is_contiguous()
+    y = torch.empty((N, cout, (H - 1) // 2 + 1, (W - 1) // 2 + 1), device=x.device,
+                    dtype=torch.float32, memory_format=torch.channels_last)
+    check(_lib.load().casmvs_conv2d_5x5s2_fp32_fwd(_ptr(xs), _ptr(w), _ptr(shift), float(slope),
+                                                   _ptr(y), N, cin, cout, H, W, _stream()),
+          "conv2d_5x5s2_fp32")
+    return y
+
+
+@_on_tensor_device
 def bias_lrelu_(x, bias, slope, round_tf32=False):
     """In-place LeakyReLU(x + bias[c]) on a channels-last (N,C,h,w) tensor (optionally stored
     TF32-rounded for a tensor-core consumer)."""

@@ -222,6 +222,11 @@ int casmvs_conv2d_5x5s2_fwd(const float* x, const float* w, const float* shift, 
                             float* y, int N, int Cin, int Cout, int H, int W, int round_tf32,
                             void* stream);
 
+/* The same blocks in the fp32 precision mode: CUDA-core FMA, bit-faithful products, output
+ * unrounded.  Same layouts; w is the plain (Cout,Cin,5,5) torch tensor (nothing is cached). */
+int casmvs_conv2d_5x5s2_fp32_fwd(const float* x, const float* w, const float* shift, float slope,
+                                 float* y, int N, int Cin, int Cout, int H, int W, void* stream);
+
 /* In-place x[...,c] = LeakyReLU(x[...,c] + bias[c]) on a channels-last tensor (C % 4 == 0):
  * the epilogue of a folded conv + eval-mode ABN block (models/modules.py:8-18). */
 int casmvs_bias_lrelu_nhwc(float* x, const float* bias, float slope, size_t numel, int C,

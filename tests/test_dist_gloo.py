@@ -81,3 +81,10 @@ def test_single_process_passthrough():
     imgs, pm, dmin, dint = make_inputs(3)
     out = sharded_depth_inference(fake_engine, imgs, pm, dmin, dint)
     assert torch.equal(out["depth_0"], fake_engine(imgs, pm, dmin, dint)["depth_0"])
+
+
+def test_single_process_empty_batch():
+    """world == 1 and B == 0 used to raise TypeError (`local` was None)."""
+    imgs, pm, dmin, dint = make_inputs(2)
+    out = sharded_depth_inference(fake_engine, imgs[:0], pm[:0], dmin[:0], dint)
+    assert out["depth_0"].shape[0] == 0 and out["confidence_2"].shape[0] == 0

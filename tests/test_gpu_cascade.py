@@ -209,14 +209,18 @@ def test_full_size_cfg2_properties():
 
 def test_feature_net_channels_last_matches_oracle():
     model, sd = build(1, "fp32")
-    x = torch.randn(2, 3, 64, 96)
+    x = torch.randn(2, 3, 64 + 32, 96)
     with torch.no_grad():
         f = model.feature(x.to(DEV))
     ref = O.feature_pyramid(x, sd)
     for k in ref:
         assert ops.is_channels_last_feats(f[k])
-        # cuDNN fp32 convs default to TF32 on B200; FeatureNet is host glue
-        assert (f[k].cpu() - ref[k]).abs().max() < 5e-2
+        # fp32 mode runs on this library's CUDA-core kernels (no cuDNN): fp32-accurate against
+        # the oracle (eval-mode ABN folded into the weights: one extra rounding per weight)
+        scale = ref[k].abs().max().item()
+        err = (f[k].cpu() - ref[k]).abs().max().item()
+        print(k, "max err / scale", err / scale)
+        assert err < 1e-5 * scale
 
 
 def test_feature_net_tensor_path_matches_fp32_path():
