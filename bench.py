@@ -224,6 +224,88 @@ def pin_to_gpu_numa(local_rank):
     return "not bound (no CPU affinity column)"
 
 
+SHARDED_CONFIGS = {
+    # BASELINE.json configs[3], configs[4]: a batch of reference views sharded over the ranks,
+    # ONE all_gather of the per-view depth maps at the end (replaces the loop at
+    # reference eval.py:213-229)
+    "cfg4": dict(W=1152, H=864, V=5, n_depths=(8, 32, 48), views_per_gpu=1),
+    "cfg5": dict(W=1920, H=1056, V=7, n_depths=(8, 32, 64), views_per_gpu=4),
+}
+
+
+def run_sharded_config(name, rank, world, dev, precision, reps=3):
+    """cfg4 / cfg5 through dist.sharded_depth_inference on `world` GPUs: ms per batch (CUDA
+    events, max over ranks, barrier on both sides, inputs resident on each rank's GPU) and
+    bit-equality of the gathered result with a single-GPU evaluation of the same views."""
+    import torch
+    import torch.distributed as dist
+    from casmvsnet_pl_b200 import ABN, synth
+    from casmvsnet_pl_b200.dist import shard_bounds, sharded_depth_inference
+    from casmvsnet_pl_b200.models.mvsnet import CascadeMVSNet
+    c = SHARDED_CONFIGS[name]
+    B = c["views_per_gpu"] * world
+    torch.manual_seed(0)
+    model = CascadeMVSNet(n_depths=list(c["n_depths"]), norm_act=ABN, precision=precision)
+    synth.randomize_model_(model, 0)
+    model = model.eval().to(dev).requires_grad_(False)
+    lo, hi = shard_bounds(B, rank, world)
+    # every rank materialises only its own shard (view i is seeded with i, so any rank can
+    # regenerate any view); the (B, ...) tensors are views of untouched virtual memory
+    shard = [synth.make_inputs(B=1, V=c["V"], W=c["W"], H=c["H"], seed=i) for i in range(lo, hi)]
+    dmin, dint = shard[0][2], shard[0][3]
+    imgs_l = torch.cat([s[0] for s in shard]).to(dev)
+    pm_l = torch.cat([s[1] for s in shard]).to(dev)
+
+    class ShardView:
+        """Stands for the (B, ...) batch: only this rank's rows exist."""
+        def __init__(self, t):
+            self.t, self.shape, self.device = t, (B,) + tuple(t.shape[1:]), t.device
+
+        def __getitem__(self, sl):
+            assert sl.start == lo and sl.stop == hi
+            return self.t
+
+    def engine(i, p, a, b):
+        with torch.no_grad():
+            return model(i, p, a, b)
+
+    def once():
+        return sharded_depth_inference(engine, ShardView(imgs_l), ShardView(pm_l), dmin, dint)
+
+    out = once()                                          # warm-up (weight packing, smem opt-in)
+    ts = []
+    for _ in range(reps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = once()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ts.append(ms.item())
+    # bit-equality with one GPU: rank 0 evaluates a view of ANOTHER rank's shard on its own GPU
+    probe = min(B - 1, hi)                                # first view of rank 1 (or last view)
+    ok = None
+    if rank == 0:
+        pi, pp, _, _ = synth.make_inputs(B=1, V=c["V"], W=c["W"], H=c["H"], seed=probe)
+        r1 = engine(pi.to(dev), pp.to(dev), dmin, dint)
+        ok = bool(torch.equal(r1["depth_0"][0], out["depth_0"][probe]) and
+                  torch.equal(r1["confidence_2"][0], out["confidence_2"][probe]) and
+                  torch.equal(out["depth_0"][lo:hi], engine(imgs_l, pm_l, dmin, dint)["depth_0"]))
+    del model
+    torch.cuda.empty_cache()
+    ts.sort()
+    return {"config": f"{name}: {c['W']}x{c['H']}, V={c['V']}, D={'/'.join(map(str, c['n_depths'][::-1]))}, "
+                      f"batch of {B} ref views over {world} GPUs ({c['views_per_gpu']}/GPU)",
+            "ms_per_batch": ts[len(ts) // 2], "views_per_s": B / (ts[len(ts) // 2] * 1e-3),
+            "gathered_shape": list(out["depth_0"].shape),
+            "bit_equal_to_single_gpu": ok,
+            "collective": "one all_gather_into_tensor per output key at the end (depth_0, confidence_2)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -234,6 +316,8 @@ def main():
                     choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-sharded-configs", action="store_true",
+                    help="skip the cfg4 / cfg5 sharded-batch runs at N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -521,6 +605,17 @@ def main():
                                   f"PyTorch-CPU path on {cores} torch threads (fastest of "
                                   f"4..{avail} available)"}
 
+    sharded = None
+    if world > 1 and not args.no_sharded_configs:
+        del graphed, pipe
+        torch.cuda.empty_cache()
+        sharded = {}
+        for name in SHARDED_CONFIGS:
+            try:
+                sharded[name] = run_sharded_config(name, rank, world, dev, args.precision)
+            except Exception as e:                                  # noqa: BLE001
+                sharded[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank == 0:
         maps = world * B * args.steps
         value = maps / (ms_total * 1e-3)
@@ -554,6 +649,7 @@ def main():
                             "(2-slot pipeline)") if pipe is not None else
                            "pinned host inputs -> H2D -> forward -> D2H, serial"},
             "parity": parity,
+            "sharded_configs": sharded,
             "fallbacks": fallbacks,
             "sustained": sustained,
             "roofline_k2": roofline_k2,

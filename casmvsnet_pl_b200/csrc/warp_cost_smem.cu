@@ -354,12 +354,20 @@ int warp_var_smem(const float* feats, const float* proj, const float* dv, float*
   if (!enabled) return 1;
   if ((reinterpret_cast<uintptr_t>(feats) & 15) != 0 || B > 65535) return 1;
   using namespace k1s;
-#define K1S(NS, CC, TW_, TH_, RU, MB) \
-  if (V - 1 == NS && C == CC) return launch<NS, CC, TW_, TH_, RU, MB>(feats, proj, dv, cost, B, D, h, w, rnd, st);
-  K1S(1, 8, 32, 4, true, 4) K1S(1, 16, 32, 4, true, 2) K1S(1, 32, 16, 4, true, 2)
-  K1S(2, 8, 32, 4, true, 4) K1S(2, 16, 32, 4, true, 2) K1S(2, 32, 16, 4, true, 2)
-  K1S(4, 8, 32, 4, false, 4) K1S(4, 16, 32, 4, false, 2) K1S(4, 32, 16, 4, false, 2)
-  K1S(6, 8, 32, 4, false, 4) K1S(6, 16, 32, 4, false, 2) K1S(6, 32, 16, 4, false, 2)
+  // tile / register-budget variants (CASMVS_K1S_VARIANT; defaults measured on cfg2, see
+  // profiles/r2_k1_variants.jsonl): {tile, REUSE windows in registers, min resident CTAs}
+  static const int variant = env_int("CASMVS_K1S_VARIANT", 0);
+#define K1S(VAR, NS, CC, TW_, TH_, RU, MB) \
+  if (variant == VAR && V - 1 == NS && C == CC) return launch<NS, CC, TW_, TH_, RU, MB>(feats, proj, dv, cost, B, D, h, w, rnd, st);
+  K1S(0, 2, 8, 32, 4, true, 4) K1S(0, 2, 16, 32, 4, true, 2) K1S(0, 2, 32, 16, 4, true, 2)
+  K1S(1, 2, 8, 32, 4, true, 3) K1S(1, 2, 16, 32, 2, true, 3) K1S(1, 2, 32, 16, 2, true, 3)
+  K1S(2, 2, 8, 32, 4, false, 4) K1S(2, 2, 16, 32, 4, false, 2) K1S(2, 2, 32, 16, 4, false, 2)
+  K1S(3, 2, 8, 32, 2, true, 6) K1S(3, 2, 16, 16, 4, true, 3) K1S(3, 2, 32, 8, 4, true, 3)
+  K1S(4, 2, 8, 32, 4, false, 5) K1S(4, 2, 16, 32, 2, false, 5) K1S(4, 2, 32, 16, 2, false, 5)
+  if (V - 1 == 2) return 1;
+  K1S(variant, 1, 8, 32, 4, true, 4) K1S(variant, 1, 16, 32, 4, true, 2) K1S(variant, 1, 32, 16, 4, true, 2)
+  K1S(variant, 4, 8, 32, 4, false, 4) K1S(variant, 4, 16, 32, 4, false, 2) K1S(variant, 4, 32, 16, 4, false, 2)
+  K1S(variant, 6, 8, 32, 4, false, 4) K1S(variant, 6, 16, 32, 4, false, 2) K1S(variant, 6, 32, 16, 4, false, 2)
 #undef K1S
   return 1;
 }

@@ -50,16 +50,21 @@ def sharded_depth_inference(engine, imgs, proj_mats, init_depth_min, depth_inter
             return {k: torch.zeros(0, 0, 0, dtype=torch.float32, device=imgs.device) for k in keys}
         return {k: local[k] for k in keys}
 
-    # every rank must know the output shapes even if its shard is empty
     cap = max_shard(B, world)
-    shapes = torch.zeros(len(keys), 2, dtype=torch.int64, device=imgs.device)
-    if local is not None:
-        for i, k in enumerate(keys):
-            shapes[i, 0], shapes[i, 1] = local[k].shape[-2:]
-    dist.all_reduce(shapes, op=dist.ReduceOp.MAX, group=group)
+    if B >= world:
+        # every rank has views: each knows the output shapes from its own results
+        shapes = [tuple(local[k].shape[-2:]) for k in keys]
+    else:
+        # some shard is empty: that rank learns the shapes from the others (control message)
+        t = torch.zeros(len(keys), 2, dtype=torch.int64, device=imgs.device)
+        if local is not None:
+            for i, k in enumerate(keys):
+                t[i, 0], t[i, 1] = local[k].shape[-2:]
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        shapes = [(int(t[i, 0]), int(t[i, 1])) for i in range(len(keys))]
     out = {}
     for i, k in enumerate(keys):
-        h, w = int(shapes[i, 0]), int(shapes[i, 1])
+        h, w = shapes[i]
         send = torch.zeros(cap, h, w, dtype=torch.float32, device=imgs.device)
         if local is not None:
             send[: hi - lo] = local[k]
