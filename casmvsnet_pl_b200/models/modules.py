@@ -57,8 +57,14 @@ class ConvBnReLU3D(nn.Module):
         return self._packed
 
     def forward(self, x):
+        if torch.is_grad_enabled() and (x.requires_grad or
+                                        any(p.requires_grad for p in self.parameters())):
+            from .. import autograd as AG
+            return self.bn(AG.conv3d(x, self.conv.weight, ops.CONV, self.conv.stride[0],
+                                     ops.PRECISIONS[self.precision]))
         if self.bn.training:
-            raise ops._lib.CasMVSError("ConvBnReLU3D is inference-only: call .eval() first")
+            raise ops._lib.CasMVSError("ConvBnReLU3D inference path needs .eval() (training runs "
+                                       "through the autograd path: enable grad)")
         w, a, b = self._params()
         return ops.conv3d(x, w, self.conv.in_channels, self.conv.out_channels, a, b,
                           activation_slope(self.bn), None, ops.CONV, self.conv.stride[0],

@@ -306,10 +306,36 @@ class CostRegNet(nn.Module):
         self._blob, self._blob_key = blob, key
         return blob
 
+    def _forward_autograd(self, x):
+        """Differentiable path (training, or eval-mode BN with parameters that require grad):
+        raw convolutions through autograd.Conv3dFn (own forward / dgrad / wgrad kernels), the
+        norm-act as the module itself (batch statistics in training mode, like InPlaceABN)."""
+        from .. import autograd as AG
+        prec = ops.PRECISIONS[self.precision]
+
+        def cbr(m, t, stride=1):
+            return m.bn(AG.conv3d(t, m.conv.weight, ops.CONV, stride, prec))
+
+        def up(m, t):
+            return m[1](AG.conv3d(t, m[0].weight, ops.CONV_TRANSPOSE, 2, prec))
+
+        conv0 = cbr(self.conv0, x)
+        conv2 = cbr(self.conv2, cbr(self.conv1, conv0, 2))
+        conv4 = cbr(self.conv4, cbr(self.conv3, conv2, 2))
+        x = cbr(self.conv6, cbr(self.conv5, conv4, 2))
+        x = conv4 + up(self.conv7, x)                                  # mvsnet.py:96-102
+        x = conv2 + up(self.conv9, x)
+        x = conv0 + up(self.conv11, x)
+        return AG.conv3d(x, self.prob.weight, ops.CONV, 1, prec) + self.prob.bias.view(1, -1, 1, 1, 1)
+
     def forward(self, x):
+        if torch.is_grad_enabled() and (x.requires_grad or
+                                        any(p.requires_grad for p in self.parameters())):
+            return self._forward_autograd(x)
         for bn in self._norm_modules():
             if bn.training:
-                raise ops._lib.CasMVSError("CostRegNet is inference-only: call .eval() first")
+                raise ops._lib.CasMVSError("CostRegNet inference path needs .eval() (training "
+                                           "runs through the autograd path: enable grad)")
             if abs(activation_slope(bn) - 0.01) > 1e-12:
                 raise ops._lib.CasMVSError("casmvs_costreg_fwd assumes LeakyReLU(0.01) norm_act")
         logits = ops.costreg(x, self.packed_params(), self.in_channels,
@@ -355,6 +381,12 @@ class CascadeMVSNet(nn.Module):
         """feats (B,V,C,h,w), proj_mats (B,V-1,3,4), depth_values (B,D,h,w),
         cost_reg: module (B,C,D,h,w)->(B,1,D,h,w).  Returns depth, confidence (B,h,w)
         (reference models/mvsnet.py:125-195)."""
+        if torch.is_grad_enabled() and (feats.requires_grad or
+                                        any(p.requires_grad for p in cost_reg.parameters())):
+            from .. import autograd as AG
+            cost = AG.warp_cost(feats, proj_mats, depth_values, self.G)
+            logits = cost_reg(cost).squeeze(1)
+            return AG.regress(logits, depth_values)
         cost = ops.warp_cost(feats, proj_mats, depth_values, self.G, ops.NHWC,
                              round_tf32=(getattr(cost_reg, "precision", "fp32") == "tf32"))
         logits = cost_reg(cost).squeeze(1)
@@ -364,6 +396,34 @@ class CascadeMVSNet(nn.Module):
         self._last_index = index
         return depth, confidence
 
+    def _forward_autograd(self, imgs, proj_mats, init_depth_min, depth_interval):
+        """The differentiable forward of the reference (mvsnet.py:197-244) for train.py:99-127:
+        FeatureNet through its torch modules (host glue), every cascade stage through the
+        autograd wrappers of K1 / K2 / K3; hypotheses are detached like mvsnet.py:231."""
+        B, V, _, H, W = imgs.shape
+        feats = self.feature(imgs.reshape(B * V, 3, H, W))
+        proj_by_level = proj_mats.permute(2, 0, 1, 3, 4).contiguous()
+        results = {}
+        depth_l = None
+        for l in reversed(range(self.levels)):
+            feats_l = feats[f"level_{l}"]
+            feats_l = feats_l.view(B, V, *feats_l.shape[1:])
+            depth_interval_l = depth_interval * self.interval_ratios[l]
+            D = self.n_depths[l]
+            h, w = feats_l.shape[-2:]
+            with torch.no_grad():
+                if l == self.levels - 1:
+                    depth_values = ops.uniform_hypotheses(init_depth_min, depth_interval_l, D, B,
+                                                          h, w, imgs.device)
+                else:
+                    depth_values = ops.depth_hypotheses(depth_l.detach(), D, depth_interval_l,
+                                                        upsample=True)
+            depth_l, confidence_l = self.predict_depth(feats_l, proj_by_level[l], depth_values,
+                                                       getattr(self, f"cost_reg_{l}"))
+            results[f"depth_{l}"] = depth_l
+            results[f"confidence_{l}"] = confidence_l
+        return results
+
     def forward(self, imgs, proj_mats, init_depth_min, depth_interval):
         """imgs (B,V,3,H,W); proj_mats (B,V-1,levels,3,4) fine->coarse;
         init_depth_min, depth_interval: float or (B,1) tensors.
@@ -372,19 +432,16 @@ class CascadeMVSNet(nn.Module):
         if not imgs.is_cuda:
             raise ops._lib.CasMVSError(
                 "CascadeMVSNet (B200 engine) needs CUDA inputs; there is no CPU fallback")
-        if torch.is_grad_enabled() and (imgs.requires_grad or
-                                        any(p.requires_grad for p in self.parameters())):
-            # the reference forward is differentiable; this engine is not.
-            # Returning detached tensors silently would train nothing, so refuse instead.
-            raise ops._lib.CasMVSError(
-                "CascadeMVSNet (B200 engine) is forward-only: call it under torch.no_grad() "
-                "(or freeze the parameters with requires_grad_(False))")
+        differentiable = torch.is_grad_enabled() and (
+            imgs.requires_grad or any(p.requires_grad for p in self.parameters()))
         # (B,1) depth parameters may arrive as CPU tensors from the reference's data loader
         # (datasets/dtu.py:188-189): move them once, not once per stage
         if torch.is_tensor(init_depth_min):
             init_depth_min = init_depth_min.to(imgs.device, torch.float32)
         if torch.is_tensor(depth_interval):
             depth_interval = depth_interval.to(imgs.device, torch.float32)
+        if differentiable:
+            return self._forward_autograd(imgs, proj_mats, init_depth_min, depth_interval)
         results = {}
         with torch.no_grad():
             feats = self.feature(imgs.reshape(B * V, 3, H, W), overlap=self.overlap_pyramid)

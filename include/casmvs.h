@@ -236,6 +236,27 @@ int casmvs_bias_lrelu_nhwc(float* x, const float* bias, float slope, size_t nume
 int casmvs_bias_act_nhwc(float* x, const float* bias, float slope, size_t numel, int C,
                          int round_tf32, void* stream);
 
+/* ---- backward of the hot path (reference train.py:99-127) -----------------
+ * casmvs_warp_cost_bwd: gradient of casmvs_warp_cost_fwd w.r.t. the features (the only
+ * differentiable input: hypotheses are detached, models/mvsnet.py:231).  All tensors
+ * channels-last: feats (B,V,h,w,C), grad_cost (B,D,h,w,Cout), grad_feats (B,V,h,w,C) which the
+ * caller ZEROES first (the bilinear taps are scattered into it with atomics).
+ * casmvs_conv3d_wgrad: grad_w[27][Ca][Cb] += sum_{b,o} x[b, stride*o + k - 1, a] * grad_y[b,o,b']
+ * for Conv3d (x = layer input, grad_y = output gradient, Ca = Cin, Cb = Cout) and, with the
+ * roles swapped (x = output gradient, grad_y = layer input, stride 2), for ConvTranspose3d;
+ * caller zeroes grad_w.  Channels <= 64.  The DATA gradients are forward kernels:
+ * conv s1 -> conv s1 with flipped/transposed weights, conv s2 -> CASMVS_CONV_TRANSPOSE,
+ * transposed -> conv s2 (casmvs_conv3d_fwd, scale = shift = NULL, slope = 1).
+ * casmvs_regress_bwd: grad_logits = softmax(logits) * (depth_values - depth) * grad_depth. */
+int casmvs_warp_cost_bwd(const float* feats, const float* proj, const float* depth_values,
+                         const float* grad_cost, float* grad_feats, int B, int V, int C, int D,
+                         int h, int w, int num_groups, void* stream);
+int casmvs_conv3d_wgrad(const float* x, const float* grad_y, float* grad_w, int B, int Ca, int Cb,
+                        int Di, int hi, int wi, int Do, int ho, int wo, int stride, void* stream);
+int casmvs_regress_bwd(const float* logits, const float* depth_values, int dv_is_vector,
+                       const float* grad_depth, float* grad_logits, int B, int D, int h, int w,
+                       void* stream);
+
 /* ---- input pipeline -------------------------------------
  * T.ToTensor() + T.Normalize(mean, std) of the reference's data sets (datasets/dtu.py:130-137)
  * for images uploaded as bytes: images (N,H,W,3) uint8 RGB -> out (N,3,H,W) float32,
