@@ -112,6 +112,86 @@ regress_kernel(const float* __restrict__ logits, const float* __restrict__ dv, i
   if (index) index[(size_t)b * hw + pix] = (long long)idx;
 }
 
+// Plane-parallel variant (the default): the generic kernel above runs ~80 instructions per
+// hypothesis in ONE thread per pixel (precise expf, IEEE division, 64-bit addressing) -- at
+// 160x128 that is 640 warps with a 3 800-instruction dependent chain each (ncu: 6.6 % of the
+// warp slots, 36 us for 7.9 MB).  Here a block owns 32 pixels and NL = 8 warps split the D
+// planes: max, exp, the division and the two products are evaluated plane-parallel; only the
+// ORDERED sums (sequential denominator, cascade-16 depth / index) are walked by one warp, from
+// shared memory.  Every value and every summation order is the generic kernel's, so the two
+// are bit-identical (tests/test_gpu_kernels.py::test_regress_register_path_bit_identical).
+constexpr int kK3Lanes = 8;
+template <bool IS_PROB>
+__global__ void __launch_bounds__(32 * kK3Lanes)
+regress_par_kernel(const float* __restrict__ logits, const float* __restrict__ dv, int dv_is_vector,
+                   float* __restrict__ depth, float* __restrict__ conf,
+                   long long* __restrict__ index, float* __restrict__ prob, int D, int hw) {
+  extern __shared__ float sh[];
+  float* P = sh;                       // [D][32]  exp, then probability
+  float* T1 = sh + (size_t)D * 32;     // [D][32]  p * depth_value
+  float* T2 = T1 + (size_t)D * 32;     // [D][32]  p * d
+  float* red = T2 + (size_t)D * 32;    // [kK3Lanes][32]
+  const int p = threadIdx.x & 31, s = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int pixr = blockIdx.x * 32 + p;
+  const bool valid = pixr < hw;
+  const int pix = valid ? pixr : hw - 1;
+  const float* lp = logits + (size_t)b * D * hw + pix;
+  const float* dp = dv_is_vector ? dv : dv + (size_t)b * D * hw + pix;
+  const size_t dstride = dv_is_vector ? 1 : (size_t)hw;
+  float m = 0.f;
+  if (!IS_PROB) {
+    float lmax = -INFINITY;
+    for (int d = s; d < D; d += kK3Lanes) {
+      const float l = __ldg(lp + (size_t)d * hw);
+      P[d * 32 + p] = l;
+      lmax = fmaxf(lmax, l);
+    }
+    red[s * 32 + p] = lmax;
+    __syncthreads();
+    m = red[p];
+#pragma unroll
+    for (int k = 1; k < kK3Lanes; ++k) m = fmaxf(m, red[k * 32 + p]);
+    for (int d = s; d < D; d += kK3Lanes) P[d * 32 + p] = expf(P[d * 32 + p] - m);
+    __syncthreads();
+    if (s == 0) {
+      float denom = 0.f;
+      for (int d = 0; d < D; ++d) denom = __fadd_rn(denom, P[d * 32 + p]);
+      red[p] = denom;
+    }
+    __syncthreads();
+  }
+  const float denom = IS_PROB ? 1.f : red[p];
+  for (int d = s; d < D; d += kK3Lanes) {
+    float pr = IS_PROB ? __ldg(lp + (size_t)d * hw) : __fdiv_rn(P[d * 32 + p], denom);
+    P[d * 32 + p] = pr;
+    T1[d * 32 + p] = __fmul_rn(pr, __ldg(dp + d * dstride));
+    T2[d * 32 + p] = __fmul_rn(pr, (float)d);
+    if (prob && valid) prob[(size_t)b * D * hw + (size_t)d * hw + pix] = pr;
+  }
+  __syncthreads();
+  if (s != 0 || !valid) return;
+  Cascade16 acc_depth, acc_idx;
+  for (int d = 0; d < D; ++d) {
+    acc_depth.add(T1[d * 32 + p]);
+    acc_idx.add(T2[d * 32 + p]);
+  }
+  const float fidx = acc_idx.result();
+  int idx;
+  if (!(fidx > 0.f)) idx = 0;
+  else if (fidx >= (float)(D - 1)) idx = D - 1;
+  else idx = (int)fidx;
+  float c = 0.f;
+#pragma unroll
+  for (int k = -1; k <= 2; ++k) {
+    const int d = idx + k;
+    c = __fadd_rn(c, (d >= 0 && d < D) ? P[d * 32 + p] : 0.f);
+  }
+  depth[(size_t)b * hw + pix] = acc_depth.result();
+  conf[(size_t)b * hw + pix] = c;
+  if (index) index[(size_t)b * hw + pix] = (long long)idx;
+}
+
 // out[b,d,y,x] = max(cur - half_range, 1e-7) + step*d, cur optionally upsampled x2
 // (align_corners=True: src = dst*(in-1)/(out-1)).
 __global__ void __launch_bounds__(256)
@@ -177,29 +257,36 @@ extern "C" int casmvs_regress_fwd(const float* logits, const float* depth_values
   if (B == 0) return 0;
   const int hw = h * w;
   cudaStream_t st = as_stream(stream);
-  static int reg_path = -1;
-  if (reg_path < 0) {
-    const char* e = getenv("CASMVS_K3_REG");
-    reg_path = e ? atoi(e) : 1;
+  static int par_path = -1;
+  if (par_path < 0) {
+    const char* e = getenv("CASMVS_K3_REG");      // 0: the one-thread-per-pixel generic kernel
+    par_path = e ? atoi(e) : 1;
+  }
+  const size_t smem = ((size_t)3 * D * 32 + kK3Lanes * 32) * sizeof(float);
+  if (par_path && smem <= 96 * 1024) {
+    dim3 grd((hw + 31) / 32, B);
+    if (input_is_prob) {
+      static std::atomic<bool> a[kMaxDevices];
+      if (int rc = opt_in_smem(regress_par_kernel<true>, 96 * 1024, a, "regress")) return rc;
+      regress_par_kernel<true><<<grd, 32 * kK3Lanes, smem, st>>>(
+          logits, depth_values, dv_is_vector, depth, confidence, (long long*)index, prob, D, hw);
+    } else {
+      static std::atomic<bool> a[kMaxDevices];
+      if (int rc = opt_in_smem(regress_par_kernel<false>, 96 * 1024, a, "regress")) return rc;
+      regress_par_kernel<false><<<grd, 32 * kK3Lanes, smem, st>>>(
+          logits, depth_values, dv_is_vector, depth, confidence, (long long*)index, prob, D, hw);
+    }
+    return after_launch("regress");
   }
   // small maps: narrower blocks so that every SM gets work
   const int threads = (long)hw * B < (long)num_sms() * 4 * kK3Threads ? 32 : kK3Threads;
   dim3 grd((hw + threads - 1) / threads, B);
-#define K3_LAUNCH(PROB, DT)                                                                   \
-  regress_kernel<PROB, DT><<<grd, threads, 0, st>>>(logits, depth_values, dv_is_vector, depth, \
-                                                    confidence, (long long*)index, prob, D, hw)
-#define K3_CASE(DT)                                    \
-  if (reg_path && D == DT) {                           \
-    if (input_is_prob) K3_LAUNCH(true, DT);            \
-    else K3_LAUNCH(false, DT);                         \
-    return after_launch("regress");                    \
-  }
-  // D = 32 (127 registers) measured slower than the generic path at 320x256: not specialised
-  K3_CASE(8) K3_CASE(48)
-  if (input_is_prob) K3_LAUNCH(true, 0);
-  else K3_LAUNCH(false, 0);
-#undef K3_CASE
-#undef K3_LAUNCH
+  if (input_is_prob)
+    regress_kernel<true, 0><<<grd, threads, 0, st>>>(logits, depth_values, dv_is_vector, depth,
+                                                     confidence, (long long*)index, prob, D, hw);
+  else
+    regress_kernel<false, 0><<<grd, threads, 0, st>>>(logits, depth_values, dv_is_vector, depth,
+                                                      confidence, (long long*)index, prob, D, hw);
   return after_launch("regress");
 }
 
