@@ -514,7 +514,7 @@ int g_k1_dchunk = 0;  // CASMVS_K1_DCHUNK overrides the depth-chunk heuristic
 
 // warp_cost_smem.cu
 int warp_var_smem(const float* feats, const float* proj, const float* dv, float* cost, int B,
-                  int V, int C, int D, int h, int w, int rnd, cudaStream_t st);
+                  int V, int C, int D, int h, int w, int num_groups, int rnd, cudaStream_t st);
 
 template <int NSRC, int CT>
 static void launch_k1(bool gwc, bool nhwc, dim3 grd, cudaStream_t st, const float* f,
@@ -609,9 +609,9 @@ extern "C" int casmvs_warp_cost_fwd(const float* feats, int feat_layout, const f
     if (const char* e = getenv("CASMVS_K1_CPT")) g_k1_cpt = atoi(e);
     if (const char* e = getenv("CASMVS_K1_SKIP")) g_k1_skip = atoi(e);
   }
-  if (!gwc && nhwc) {
+  if (nhwc) {
     // TMA-staged generation (warp_cost_smem.cu): 0 = handled, 1 = shape left to the gather kernels
-    const int rc = warp_var_smem(f, proj, depth_values, cost, B, V, C, D, h, w, rnd, st);
+    const int rc = warp_var_smem(f, proj, depth_values, cost, B, V, C, D, h, w, num_groups, rnd, st);
     if (rc <= 0) return rc;
   }
   if (!gwc && nhwc && (V == 3 || V == 2) && (C == 8 || C == 16 || C == 32) &&

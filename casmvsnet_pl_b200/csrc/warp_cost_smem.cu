@@ -66,13 +66,16 @@ struct Small {            // lives behind the boxes in dynamic shared memory
 
 // NSRC source views, C channels (8 per thread), TW x TH pixel tile; REUSE: keep the 2x2 windows
 // in registers across planes (64 registers at NSRC = 2).
-template <int NSRC, int C, int TW, int TH, bool REUSE, int MINB>
+template <int NSRC, int C, int TW, int TH, bool REUSE, int MINB, bool GWC = false>
 __global__ void __launch_bounds__(TW* TH*(C / kCPT), MINB)
 warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __restrict__ feats,
                      const float* __restrict__ proj, const float* __restrict__ dv,
                      float* __restrict__ cost, int D, int h, int w, int dchunk, int BW, int BH,
                      int box_stride, int tiles_x, int round_tf32) {
+  // GWC (group-wise correlation, mvsnet.py:143-144,158-162,170-172) is built for 8 groups:
+  // C/8 in {1,2,4} channels per group, every thread owns 8/(C/8) whole groups
   constexpr int V = NSRC + 1, TPP = C / kCPT, TEXB = C * 4, NT = TW * TH * TPP;
+  constexpr int CPG = C / 8, NG = kCPT / CPG, COUT = GWC ? 8 : C;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   Small* sm = reinterpret_cast<Small*>(smem_raw + (base - smem_u32(smem_raw)) + NSRC * box_stride);
@@ -115,7 +118,7 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
   const int d_begin = blockIdx.z * dchunk;
   const int d_end = min(D, d_begin + dchunk);
   const float* dvp = dv + (size_t)b * D * hw + pix;
-  float* optr = cost + ((size_t)(b * D + d_begin) * hw + pix) * C + c0;
+  float* optr = cost + ((size_t)(b * D + d_begin) * hw + pix) * COUT + (GWC ? sub * NG : c0);
   const int row_b = BW * TEXB;
 
   Tex8 t00[NSRC], t01[NSRC], t10[NSRC], t11[NSRC];
@@ -197,7 +200,10 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
       if (d + 1 < d0 + n) depth_next = __ldg(dptr);
       u64 S[4], Q[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { S[k] = ref.v[k]; Q[k] = mul2(ref.v[k], ref.v[k]); }
+      for (int k = 0; k < 4; ++k) {
+        S[k] = GWC ? 0ull : ref.v[k];            // gwc: the reference is NOT in the sum (:144)
+        Q[k] = mul2(ref.v[k], ref.v[k]);
+      }
 #pragma unroll
       for (int v = 0; v < NSRC; ++v) {
         const float qx = fmaf(tx[v], inv_d, ax[v]);
@@ -256,8 +262,33 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           S[k] = add2(S[k], r[k]);
-          Q[k] = fma2(r[k], r[k], Q[k]);
+          if (!GWC) Q[k] = fma2(r[k], r[k], Q[k]);
         }
+      }
+      if constexpr (GWC) {
+        // cost[g] = mean_{c in g}(S_c * ref_c) / (V-1)     (mvsnet.py:170-172)
+        float pr[kCPT], o[NG];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) unpk2(mul2(S[k], ref.v[k]), pr[2 * k], pr[2 * k + 1]);
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+          float acc = CPG == 1 ? pr[k] : CPG == 2 ? pr[2 * k] + pr[2 * k + 1]
+                      : (pr[4 * k] + pr[4 * k + 1]) + (pr[4 * k + 2] + pr[4 * k + 3]);
+          float val = __fdiv_rn(acc * (1.f / (float)CPG), (float)NSRC);
+          o[k] = round_tf32 ? round_tf32_f(val) : val;
+        }
+        if (active) {
+          if constexpr (NG == 8) {
+            u64 ov[4] = {pk2(o[0], o[1]), pk2(o[2], o[3]), pk2(o[4], o[5]), pk2(o[6], o[7])};
+            stg256(optr, ov);
+          } else if constexpr (NG == 4) {
+            st4(optr, make_float4(o[0], o[1], o[2], o[3]));
+          } else {
+            *reinterpret_cast<float2*>(optr) = make_float2(o[0], o[1]);
+          }
+        }
+        optr += (size_t)hw * COUT;
+        continue;
       }
       // var = Q/V - (S/V)^2   (mvsnet.py:166-168)
       u64 o[4];
@@ -314,7 +345,7 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int NSRC, int C, int TW, int TH, bool REUSE, int MINB>
+template <int NSRC, int C, int TW, int TH, bool REUSE, int MINB, bool GWC = false>
 static int launch(const float* feats, const float* proj, const float* dv, float* cost, int B, int D,
                   int h, int w, int rnd, cudaStream_t st) {
   constexpr int NT = TW * TH * (C / kCPT);
@@ -325,7 +356,7 @@ static int launch(const float* feats, const float* proj, const float* dv, float*
   const int BW = TW + mx, BH = TH + my;
   const int box_stride = (BW * BH * C * 4 + 1023) & ~1023;
   const size_t smem = (size_t)NSRC * box_stride + sizeof(Small) + 1024;
-  auto kfn = warp_var_smem_kernel<NSRC, C, TW, TH, REUSE, MINB>;
+  auto kfn = warp_var_smem_kernel<NSRC, C, TW, TH, REUSE, MINB, GWC>;
   static std::atomic<bool> attr_set[kMaxDevices];
   if (int rc = opt_in_smem(kfn, 200 * 1024, attr_set, "warp_cost")) return rc;
   if (smem > 200 * 1024) return 1;
@@ -349,11 +380,21 @@ static int launch(const float* feats, const float* proj, const float* dv, float*
 // Variance cost volume, channels-last features and output.  Returns 0 when handled, 1 when the
 // shape is left to the gather kernels of warp_cost.cu, <0 on error.
 int warp_var_smem(const float* feats, const float* proj, const float* dv, float* cost, int B,
-                  int V, int C, int D, int h, int w, int rnd, cudaStream_t st) {
+                  int V, int C, int D, int h, int w, int num_groups, int rnd, cudaStream_t st) {
   static const int enabled = k1s::env_int("CASMVS_K1_SMEM", 1);
   if (!enabled) return 1;
   if ((reinterpret_cast<uintptr_t>(feats) & 15) != 0 || B > 65535) return 1;
   using namespace k1s;
+  if (num_groups != 1) {
+    // group-wise correlation: the reference's default G = 8, source views as in cfg3
+    if (num_groups != 8) return 1;
+#define K1G(NS, CC, TW_, TH_, MB) \
+  if (V - 1 == NS && C == CC) return launch<NS, CC, TW_, TH_, NS <= 2, MB, true>(feats, proj, dv, cost, B, D, h, w, rnd, st);
+    K1G(2, 8, 32, 4, 4) K1G(2, 16, 32, 4, 2) K1G(2, 32, 16, 4, 2)
+    K1G(4, 8, 32, 4, 4) K1G(4, 16, 32, 4, 2) K1G(4, 32, 16, 4, 2)
+#undef K1G
+    return 1;
+  }
   // tile / register-budget variants (CASMVS_K1S_VARIANT; defaults measured on cfg2, see
   // profiles/r2_k1_variants.jsonl): {tile, REUSE windows in registers, min resident CTAs}
   static const int variant = env_int("CASMVS_K1S_VARIANT", 0);
