@@ -12,6 +12,8 @@ import sys
 
 import torch
 
+torch.set_grad_enabled(False)   # inference scripts: the fused (non-autograd) path
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from casmvsnet_pl_b200 import ops, synth   # noqa: E402
@@ -73,7 +75,9 @@ for l, D in ((2, 48), (1, 32), (0, 8)):
                     GBps=round(nbytes / ms / 1e6, 1), frac=round(nbytes / ms / 1e6 / peak, 3),
                     checksum=float(o.double().abs().sum())))
 if not a.profile:
-    print(json.dumps(dict(cache=os.environ.get("CASMVS_K1_CACHE", "1"),
-                          dchunk=os.environ.get("CASMVS_K1_DCHUNK", "auto"), views=V, gwc=a.gwc,
+    print(json.dumps(dict(smem=os.environ.get("CASMVS_K1_SMEM", "1"),
+                          variant=os.environ.get("CASMVS_K1S_VARIANT", "0"),
+                          margin=os.environ.get("CASMVS_K1_MARGIN_X", "dflt"),
+                          dchunk=os.environ.get("CASMVS_K1S_DCHUNK", "auto"), views=V, gwc=a.gwc,
                           total_ms=round(tot_ms, 4), GBps=round(tot_b / tot_ms / 1e6, 1),
                           frac_of_peak=round(tot_b / tot_ms / 1e6 / peak, 3), peak=peak, levels=out)))

@@ -3,6 +3,8 @@ cfg3 640x512 V=3 gwc G=8; cfg4 1152x864 V=5; cfg5 1920x1056 V=7 D=64/32/8.
 Checks finiteness, and at level 2 compares K1 against the CPU oracle (seconds at these sizes)."""
 import os, sys, time, json
 import torch
+
+torch.set_grad_enabled(False)   # inference scripts: the fused (non-autograd) path
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from casmvsnet_pl_b200 import ABN, ops, synth

@@ -5,6 +5,8 @@ import sys
 
 import torch
 
+torch.set_grad_enabled(False)   # inference scripts: the fused (non-autograd) path
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from casmvsnet_pl_b200 import ABN, synth                      # noqa: E402

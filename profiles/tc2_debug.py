@@ -1,6 +1,8 @@
 """tcgen05 stride-2 / transposed conv bring-up: TF32 tensor-core path vs fp32 CUDA cores."""
 import os, sys
 import torch
+
+torch.set_grad_enabled(False)   # inference scripts: the fused (non-autograd) path
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from casmvsnet_pl_b200 import ops

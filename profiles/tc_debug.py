@@ -1,6 +1,8 @@
 """tcgen05 conv bring-up: TC (tf32) vs CUDA-core fp32 on random volumes."""
 import sys, os
 import torch
+
+torch.set_grad_enabled(False)   # inference scripts: the fused (non-autograd) path
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from casmvsnet_pl_b200 import ops

@@ -1,6 +1,8 @@
 """Run every tensor-core-eligible CostRegNet layer shape of cfg2 once (hang finder / timer)."""
 import os, sys, time
 import torch
+
+torch.set_grad_enabled(False)   # inference scripts: the fused (non-autograd) path
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from casmvsnet_pl_b200 import ops

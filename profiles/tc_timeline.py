@@ -1,6 +1,8 @@
 """Per-role clock64 timeline of CTA 0 of the tcgen05 conv kernel (debug aid)."""
 import os, sys
 import torch
+
+torch.set_grad_enabled(False)   # inference scripts: the fused (non-autograd) path
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 dev = "cuda:0"

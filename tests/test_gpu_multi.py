@@ -17,6 +17,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
+    torch.set_grad_enabled(False)            # inference, like eval.py:219
     dist.init_process_group("nccl", rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
     try:
