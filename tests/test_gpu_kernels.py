@@ -183,7 +183,8 @@ def test_cost_volume_smem_staging_paths(V, C, level, case):
     # white-noise texels: the reference's own normalise/un-normalise round trip moves a sample by
     # a few ulp(u) (~2e-5 px at w=640) -> up to ~3e-4 on a variance of magnitude ~10
     assert err.max() < 5e-5 * want.abs().max().item() + 1e-4
-    assert err.mean() < 2e-6
+    # (a wrong tap, weight or box offset gives O(1) errors; ulp-level position noise ~1e-5)
+    assert err.mean() < 1e-4
 
 
 # ----------------------------------------------------------------------------- K2
