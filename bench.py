@@ -460,153 +460,167 @@ def main():
                      "what": "CUDA-graph replays of the resident step back to back, no collective"}
     fallbacks = _lib.fallback_count() - fb0
 
+    extras_failed = {}
     # ---- K1 roofline: the three launches of one depth map, CUDA events, L2 flushed ----
     roofline = None
     hot = None
     if rank == 0:
-        peak, peak_src = measured_peak_hbm()
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-        per_stage_bytes = k1_algorithmic_bytes(VIEWS)
-        stage_ms = []
-        with torch.no_grad():
-            feats = model.feature(imgs_d.reshape(B * VIEWS, 3, H_IMG, W_IMG))
-            for i, l in enumerate((2, 1, 0)):
-                f = feats[f"level_{l}"]
-                f = f.view(B, VIEWS, *f.shape[1:])
-                D = N_DEPTHS[l]
-                h, w = f.shape[-2:]
-                dv = ops.uniform_hypotheses(dmin + 3.0 * l, dint * RATIOS[l], D, B, h, w, dev)
-                pml = pm_d[:, :, l].contiguous()
-                ts = []
-                for it in range(3 + 10):
-                    flush.zero_()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    ops.warp_cost(f, pml, dv, 1, ops.NHWC)
-                    e1.record()
-                    torch.cuda.synchronize()
-                    if it >= 3:
-                        ts.append(e0.elapsed_time(e1))
-                stage_ms.append(sum(ts) / len(ts))
-        tot_bytes = sum(per_stage_bytes)
-        tot_ms = sum(stage_ms)
-        achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
-        roofline = {"kernel": "warp_cost_kernel (K1, fused warp+variance), 3 launches / depth map",
-                    "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "per_stage": [{"level": l, "algorithmic_bytes": b, "ms": m,
-                                   "GBps": b / (m * 1e-3) / 1e9}
-                                  for l, b, m in zip((2, 1, 0), per_stage_bytes, stage_ms)],
-                    "l2": "flushed (256 MiB memset) before every timed launch"}
-        prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
-        if os.path.isfile(prof):
-            try:
-                roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_depth_map")
-            except Exception:
-                pass
-        # hot path only (features resident): K4+K1+K2+K3 x 3 stages
-        def hot_only():
-            depth_l = None
-            for l in (2, 1, 0):
-                f = feats[f"level_{l}"]
-                f = f.view(B, VIEWS, *f.shape[1:])
-                D = N_DEPTHS[l]
-                h, w = f.shape[-2:]
-                if l == 2:
-                    dv = ops.uniform_hypotheses(dmin, dint * RATIOS[l], D, B, h, w, dev)
-                else:
-                    dv = ops.depth_hypotheses(depth_l, D, dint * RATIOS[l], upsample=True)
-                depth_l, _ = model.predict_depth(f, pm_d[:, :, l], dv, getattr(model, f"cost_reg_{l}"))
-        with torch.no_grad():
-            for _ in range(3):
-                hot_only()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(args.steps):
-                hot_only()
-            e1.record()
-            torch.cuda.synchronize()
-            hot_ms = e0.elapsed_time(e1) / args.steps
-        hot = {"ms_per_depth_map": hot_ms, "depth_maps_per_s": 1e3 / hot_ms,
-               "what": "features resident -> depth/confidence (K4,K1,K2,K3 x 3 stages), no FeatureNet"}
+        try:
+            peak, peak_src = measured_peak_hbm()
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+            per_stage_bytes = k1_algorithmic_bytes(VIEWS)
+            stage_ms = []
+            with torch.no_grad():
+                feats = model.feature(imgs_d.reshape(B * VIEWS, 3, H_IMG, W_IMG))
+                for i, l in enumerate((2, 1, 0)):
+                    f = feats[f"level_{l}"]
+                    f = f.view(B, VIEWS, *f.shape[1:])
+                    D = N_DEPTHS[l]
+                    h, w = f.shape[-2:]
+                    dv = ops.uniform_hypotheses(dmin + 3.0 * l, dint * RATIOS[l], D, B, h, w, dev)
+                    pml = pm_d[:, :, l].contiguous()
+                    ts = []
+                    for it in range(3 + 10):
+                        flush.zero_()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        ops.warp_cost(f, pml, dv, 1, ops.NHWC)
+                        e1.record()
+                        torch.cuda.synchronize()
+                        if it >= 3:
+                            ts.append(e0.elapsed_time(e1))
+                    stage_ms.append(sum(ts) / len(ts))
+            tot_bytes = sum(per_stage_bytes)
+            tot_ms = sum(stage_ms)
+            achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
+            roofline = {"kernel": "warp_cost_kernel (K1, fused warp+variance), 3 launches / depth map",
+                        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "per_stage": [{"level": l, "algorithmic_bytes": b, "ms": m,
+                                       "GBps": b / (m * 1e-3) / 1e9}
+                                      for l, b, m in zip((2, 1, 0), per_stage_bytes, stage_ms)],
+                        "l2": "flushed (256 MiB memset) before every timed launch"}
+            prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
+            if os.path.isfile(prof):
+                try:
+                    roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_depth_map")
+                except Exception:
+                    pass
+            # hot path only (features resident): K4+K1+K2+K3 x 3 stages
+            def hot_only():
+                depth_l = None
+                for l in (2, 1, 0):
+                    f = feats[f"level_{l}"]
+                    f = f.view(B, VIEWS, *f.shape[1:])
+                    D = N_DEPTHS[l]
+                    h, w = f.shape[-2:]
+                    if l == 2:
+                        dv = ops.uniform_hypotheses(dmin, dint * RATIOS[l], D, B, h, w, dev)
+                    else:
+                        dv = ops.depth_hypotheses(depth_l, D, dint * RATIOS[l], upsample=True)
+                    depth_l, _ = model.predict_depth(f, pm_d[:, :, l], dv, getattr(model, f"cost_reg_{l}"))
+            with torch.no_grad():
+                for _ in range(3):
+                    hot_only()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(args.steps):
+                    hot_only()
+                e1.record()
+                torch.cuda.synchronize()
+                hot_ms = e0.elapsed_time(e1) / args.steps
+            hot = {"ms_per_depth_map": hot_ms, "depth_maps_per_s": 1e3 / hot_ms,
+                   "what": "features resident -> depth/confidence (K4,K1,K2,K3 x 3 stages), no FeatureNet"}
+        except Exception as e:                                       # noqa: BLE001
+            extras_failed["roofline_k1"] = f"{type(e).__name__}: {e}"[:300]
+            print(f"WARNING: bench extra 'roofline_k1' failed: {e}", file=sys.stderr)
 
     # ---- K2 roofline: the three CostRegNet stacks (11 layers each), CUDA events, L2 flushed
     roofline_k2 = None
     if rank == 0:
-        stage_ms = []
-        with torch.no_grad():
-            for l in (2, 1, 0):
-                f = feats[f"level_{l}"]
-                f = f.view(B, VIEWS, *f.shape[1:])
-                D = N_DEPTHS[l]
-                h, w = f.shape[-2:]
-                dv = ops.uniform_hypotheses(dmin + 3.0 * l, dint * RATIOS[l], D, B, h, w, dev)
-                cost = ops.warp_cost(f, pm_d[:, :, l].contiguous(), dv, 1, ops.NHWC,
-                                     round_tf32=(args.precision == "tf32"))
-                reg = getattr(model, f"cost_reg_{l}")
-                ts = []
-                for it in range(3 + 10):
-                    flush.zero_()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    reg(cost)
-                    e1.record()
-                    torch.cuda.synchronize()
-                    if it >= 3:
-                        ts.append(e0.elapsed_time(e1))
-                stage_ms.append(sum(ts) / len(ts))
-                del cost
-        k2_ms = sum(stage_ms)
-        roofline_k2 = {"kernel": "CostRegNet x3 (33 tcgen05 conv launches / depth map)",
-                       "algorithmic_bytes": K2_ALGO_BYTES, "flop": K2_ALGO_FLOP, "ms": k2_ms,
-                       "per_stage_ms": dict(zip(("level_2", "level_1", "level_0"), stage_ms)),
-                       "GBps": K2_ALGO_BYTES / (k2_ms * 1e-3) / 1e9,
-                       "frac_hbm": K2_ALGO_BYTES / (k2_ms * 1e-3) / 1e9 / peak,
-                       "TFLOPps": K2_ALGO_FLOP / (k2_ms * 1e-3) / 1e12,
-                       "bound": "hbm (fp32 activations, Cout <= 64: 44 FLOP/B << ridge)",
-                       "tensor_pipe_pct": None,
-                       "l2": "flushed before every timed stack"}
-        prof = os.path.join(ROOT, "profiles", "k2_tensor_pipe.json")
-        if os.path.isfile(prof):
-            try:
-                roofline_k2["tensor_pipe_pct"] = json.load(open(prof))
-            except Exception:
-                pass
+        try:
+            stage_ms = []
+            with torch.no_grad():
+                for l in (2, 1, 0):
+                    f = feats[f"level_{l}"]
+                    f = f.view(B, VIEWS, *f.shape[1:])
+                    D = N_DEPTHS[l]
+                    h, w = f.shape[-2:]
+                    dv = ops.uniform_hypotheses(dmin + 3.0 * l, dint * RATIOS[l], D, B, h, w, dev)
+                    cost = ops.warp_cost(f, pm_d[:, :, l].contiguous(), dv, 1, ops.NHWC,
+                                         round_tf32=(args.precision == "tf32"))
+                    reg = getattr(model, f"cost_reg_{l}")
+                    ts = []
+                    for it in range(3 + 10):
+                        flush.zero_()
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        reg(cost)
+                        e1.record()
+                        torch.cuda.synchronize()
+                        if it >= 3:
+                            ts.append(e0.elapsed_time(e1))
+                    stage_ms.append(sum(ts) / len(ts))
+                    del cost
+            k2_ms = sum(stage_ms)
+            roofline_k2 = {"kernel": "CostRegNet x3 (33 tcgen05 conv launches / depth map)",
+                           "algorithmic_bytes": K2_ALGO_BYTES, "flop": K2_ALGO_FLOP, "ms": k2_ms,
+                           "per_stage_ms": dict(zip(("level_2", "level_1", "level_0"), stage_ms)),
+                           "GBps": K2_ALGO_BYTES / (k2_ms * 1e-3) / 1e9,
+                           "frac_hbm": K2_ALGO_BYTES / (k2_ms * 1e-3) / 1e9 / peak,
+                           "TFLOPps": K2_ALGO_FLOP / (k2_ms * 1e-3) / 1e12,
+                           "bound": "hbm (fp32 activations, Cout <= 64: 44 FLOP/B << ridge)",
+                           "tensor_pipe_pct": None,
+                           "l2": "flushed before every timed stack"}
+            prof = os.path.join(ROOT, "profiles", "k2_tensor_pipe.json")
+            if os.path.isfile(prof):
+                try:
+                    roofline_k2["tensor_pipe_pct"] = json.load(open(prof))
+                except Exception:
+                    pass
+        except Exception as e:                                       # noqa: BLE001
+            extras_failed["roofline_k2"] = f"{type(e).__name__}: {e}"[:300]
+            print(f"WARNING: bench extra 'roofline_k2' failed: {e}", file=sys.stderr)
 
     cpu_baseline = None
     parity = None
     if rank == 0 and not args.no_cpu_baseline and world == 1:
-        avail = len(os.sched_getaffinity(0))
-        cores = best_cpu_threads(avail)
-        med, total, ref_out = time_cpu_port(3, 1, cores, want_result=True)
-        # parity of THIS run's GPU output against the oracle on the same seed-0 inputs/weights
-        with torch.no_grad():
-            got = graphed() if graphed is not None else model(imgs_d, pm_d, dmin, dint)
-        torch.cuda.synchronize()
-        parity = {}
-        for l in (2, 1, 0):
-            d, r = got[f"depth_{l}"].cpu(), ref_out[f"depth_{l}"]
-            parity[f"rel_l1_depth_{l}"] = ((d - r).abs().mean() / r.abs().mean()).item()
-        gen = torch.Generator().manual_seed(1)
-        gt = ref_out["depth_0"] + 5.6 * torch.randn(ref_out["depth_0"].shape, generator=gen)
-        a = (got["depth_0"].cpu() - gt).abs().mean().item()
-        b = (ref_out["depth_0"] - gt).abs().mean().item()
-        parity.update({"rel_l1": parity["rel_l1_depth_0"], "abs_err_ours_mm": a,
-                       "abs_err_oracle_mm": b, "abs_err_delta": abs(a - b),
-                       "confidence_2_max_delta": (got["confidence_2"].cpu() -
-                                                  ref_out["confidence_2"]).abs().max().item(),
-                       "against": "oracle.cascade_forward on the same seed-0 inputs and weights "
-                                  "(the cpu_baseline run)", "tolerance": "rel_l1 < 1e-3 (north_star)"})
-        parity["ok"] = bool(parity["rel_l1"] < 1e-3 and parity["abs_err_delta"] < 1e-3)
-        if not parity["ok"]:
-            print(f"WARNING: parity against the oracle FAILED: {parity}", file=sys.stderr)
-        cpu_baseline = {"value": 1.0 / med, "unit": "depth-maps/s", "cores": cores, "kind": "port",
-                        "sample": "1 warm-up + 3 timed full forwards of the same cfg2 workload "
-                                  f"(median {med:.2f} s/depth-map), oracle port of the reference "
-                                  f"PyTorch-CPU path on {cores} torch threads (fastest of "
-                                  f"4..{avail} available)"}
+        try:
+            avail = len(os.sched_getaffinity(0))
+            cores = best_cpu_threads(avail)
+            med, total, ref_out = time_cpu_port(3, 1, cores, want_result=True)
+            # parity of THIS run's GPU output against the oracle on the same seed-0 inputs/weights
+            with torch.no_grad():
+                got = graphed() if graphed is not None else model(imgs_d, pm_d, dmin, dint)
+            torch.cuda.synchronize()
+            parity = {}
+            for l in (2, 1, 0):
+                d, r = got[f"depth_{l}"].cpu(), ref_out[f"depth_{l}"]
+                parity[f"rel_l1_depth_{l}"] = ((d - r).abs().mean() / r.abs().mean()).item()
+            gen = torch.Generator().manual_seed(1)
+            gt = ref_out["depth_0"] + 5.6 * torch.randn(ref_out["depth_0"].shape, generator=gen)
+            a = (got["depth_0"].cpu() - gt).abs().mean().item()
+            b = (ref_out["depth_0"] - gt).abs().mean().item()
+            parity.update({"rel_l1": parity["rel_l1_depth_0"], "abs_err_ours_mm": a,
+                           "abs_err_oracle_mm": b, "abs_err_delta": abs(a - b),
+                           "confidence_2_max_delta": (got["confidence_2"].cpu() -
+                                                      ref_out["confidence_2"]).abs().max().item(),
+                           "against": "oracle.cascade_forward on the same seed-0 inputs and weights "
+                                      "(the cpu_baseline run)", "tolerance": "rel_l1 < 1e-3 (north_star)"})
+            parity["ok"] = bool(parity["rel_l1"] < 1e-3 and parity["abs_err_delta"] < 1e-3)
+            if not parity["ok"]:
+                print(f"WARNING: parity against the oracle FAILED: {parity}", file=sys.stderr)
+            cpu_baseline = {"value": 1.0 / med, "unit": "depth-maps/s", "cores": cores, "kind": "port",
+                            "sample": "1 warm-up + 3 timed full forwards of the same cfg2 workload "
+                                      f"(median {med:.2f} s/depth-map), oracle port of the reference "
+                                      f"PyTorch-CPU path on {cores} torch threads (fastest of "
+                                      f"4..{avail} available)"}
+        except Exception as e:                                       # noqa: BLE001
+            extras_failed["cpu_baseline_parity"] = f"{type(e).__name__}: {e}"[:300]
+            print(f"WARNING: bench extra 'cpu_baseline_parity' failed: {e}", file=sys.stderr)
 
+    pipelined = pipe is not None
     sharded = None
     if world > 1 and not args.no_sharded_configs:
         del graphed, pipe
@@ -648,9 +662,10 @@ def main():
                     "ms_per_step": ms_e2e / args.steps,
                     "how": ("pinned host inputs -> H2D -> CUDA-graph forward -> D2H of depth_0 + "
                             "confidence_2, every step; copies of neighbouring steps overlap compute "
-                            "(2-slot pipeline)") if pipe is not None else
+                            "(2-slot pipeline)") if pipelined else
                            "pinned host inputs -> H2D -> forward -> D2H, serial"},
             "parity": parity,
+            "extras_failed": extras_failed or None,
             "sharded_configs": sharded,
             "fallbacks": fallbacks,
             "sustained": sustained,
