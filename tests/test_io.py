@@ -119,3 +119,44 @@ def test_infer_views_writes_reference_layout(tmp_path):
         c, _ = cio.read_pfm(tmp_path / "depth" / scan / f"proba_{vid:04d}.pfm")
         assert np.array_equal(d, res["depth_0"][0].cpu().numpy())
         assert np.array_equal(c, res["confidence_2"][0].cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_eval_pipeline_on_a_synthetic_scan(tmp_path):
+    """eval.py end to end (depth inference -> filter -> fusion -> PLY / PFM) on a small scan written
+    in the DTU test layout: images as PNG, MVSNet cam files, pair.txt."""
+    cv2 = pytest.importorskip("cv2")
+    from casmvsnet_pl_b200 import ABN, eval_pipeline, synth
+    from casmvsnet_pl_b200.models.mvsnet import CascadeMVSNet
+    root = tmp_path / "dtu"
+    (root / "Cameras").mkdir(parents=True)
+    (root / "Rectified" / "scan7").mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    W, H, n = 160, 128, 4
+    K4 = synth.intrinsics(0, W, H)      # cam files hold full-resolution intrinsics (dtu.py:61-63)
+    for vid in range(n):
+        t = np.deg2rad(3.0 * vid)
+        E = np.eye(4)
+        E[:3, :3] = [[np.cos(t), 0, np.sin(t)], [0, 1, 0], [-np.sin(t), 0, np.cos(t)]]
+        E[:3, 3] = [-680 * np.sin(t), 0, 680 * (1 - np.cos(t))]
+        rows = ["extrinsic"] + [" ".join(f"{v:.6f}" for v in r) for r in E] + ["", "intrinsic"]
+        rows += [" ".join(f"{v:.6f}" for v in r) for r in K4] + ["", "425.0 2.65"]
+        (root / "Cameras" / f"{vid:08d}_cam.txt").write_text("\n".join(rows) + "\n")
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        cv2.imwrite(str(root / "Rectified" / "scan7" / f"rect_{vid + 1:03d}_3_r5000.png"), img)
+    (root / "Cameras" / "pair.txt").write_text(
+        "4\n0\n3 1 9.0 2 8.0 3 7.0\n1\n3 0 9.0 2 8.0 3 7.0\n2\n3 1 9.0 3 8.0 0 7.0\n3\n3 2 9.0 1 8.0 0 7.0\n")
+    torch.manual_seed(0)
+    model = CascadeMVSNet(norm_act=ABN, precision="tf32")
+    synth.randomize_model_(model, 0)
+    model = model.eval().cuda()
+    scan = eval_pipeline.DTUTestScan(str(root), "scan7", (W, H), n_views=3, full_wh=(W, H))
+    xyz, rgb = eval_pipeline.run_scan(model, scan, conf=0.0, min_geo_consistent=0,
+                                      depth_dir=str(tmp_path / "depth"), ply_path=str(tmp_path / "s.ply"))
+    assert xyz.shape[1] == 3 and len(xyz) == len(rgb) == n * H * W      # nothing filtered out
+    d, _ = cio.read_pfm(tmp_path / "depth" / "scan7" / "depth_0002.pfm")
+    assert d.shape == (H, W) and np.isfinite(d).all() and d.min() > 300
+    assert os.path.getsize(tmp_path / "s.ply") > 15 * len(xyz)
+    # with the reference's thresholds random images are (almost) never consistent in 5 views
+    xyz2, _ = eval_pipeline.run_scan(model, scan, conf=0.999, min_geo_consistent=5)
+    assert len(xyz2) < len(xyz)
