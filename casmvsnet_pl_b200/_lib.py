@@ -51,6 +51,12 @@ SIGNATURES = {
                                             c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "casmvs_uniform_hypotheses_fwd": (c_int, [c_float, c_float, c_void_p, c_void_p, c_void_p,
                                               c_int, c_int, c_int, c_int, c_void_p]),
+    "casmvs_depth_first_fwd": (c_int, [c_void_p, c_int, c_float, c_float, c_void_p, c_void_p,
+                                       c_int, c_int, c_int, c_int, c_void_p]),
+    "casmvs_warp_cost_ladder_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                                            c_float, c_void_p] + [c_int] * 8 + [c_void_p]),
+    "casmvs_regress_ladder_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_float,
+                                          c_void_p, c_void_p, c_void_p] + [c_int] * 4 + [c_void_p]),
     "casmvs_fpn_level_fwd": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_void_p]),
     "casmvs_fpn_merge_fwd": (c_int, [c_void_p] * 5 + [c_int] * 5 + [c_void_p]),
     "casmvs_conv2d_rgb8_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p] + [c_int] * 4 + [c_void_p]),

@@ -93,4 +93,29 @@ __device__ __forceinline__ void sample_view(const float* __restrict__ vbase, flo
 }
 
 
+// Where a pixel's depth hypotheses come from: the (B,D,h,w) tensor of the public API, or -- in
+// the cascade -- the ladder first + step*d that get_depth_values / the initial planes define
+// (models/modules.py:44-48, models/mvsnet.py:215-229), generated in the kernel with the SAME two
+// roundings (multiply, then add) so that the (B,D,h,w) tensor never has to exist in HBM.
+struct Hyp {
+  const float* dv;         // (B,D,h,w) or null => ladder
+  const float* first_map;  // (B,h,w) first hypothesis per pixel, or null
+  const float* first_b;    // (B) first hypothesis per batch item, or null
+  const float* step_b;     // (B) plane spacing per batch item, or null
+  float first, step;       // scalars used when the pointers above are null
+};
+struct HypPix {
+  const float* p;
+  size_t hw;
+  float first, step;
+  __device__ __forceinline__ HypPix(const Hyp& h, int b, int D, size_t hw_, int pix) : hw(hw_) {
+    p = h.dv ? h.dv + (size_t)b * D * hw_ + pix : nullptr;
+    first = h.first_map ? __ldg(h.first_map + (size_t)b * hw_ + pix) : h.first_b ? __ldg(h.first_b + b) : h.first;
+    step = h.step_b ? __ldg(h.step_b + b) : h.step;
+  }
+  __device__ __forceinline__ float at(int d) const {
+    return p ? __ldg(p + (size_t)d * hw) : __fadd_rn(first, __fmul_rn(step, (float)d));
+  }
+};
+
 }  // namespace casmvs

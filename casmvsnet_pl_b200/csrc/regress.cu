@@ -9,7 +9,7 @@
 //   initial uniform planes          models/mvsnet.py:213-229
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "k1_common.cuh"
 
 namespace casmvs {
 
@@ -124,7 +124,7 @@ constexpr int kK3Lanes = 8;
 template <bool IS_PROB>
 __global__ void __launch_bounds__(32 * kK3Lanes)
 regress_par_kernel(const float* __restrict__ logits, const float* __restrict__ dv, int dv_is_vector,
-                   float* __restrict__ depth, float* __restrict__ conf,
+                   const Hyp hyp, float* __restrict__ depth, float* __restrict__ conf,
                    long long* __restrict__ index, float* __restrict__ prob, int D, int hw) {
   extern __shared__ float sh[];
   float* P = sh;                       // [D][32]  exp, then probability
@@ -137,8 +137,10 @@ regress_par_kernel(const float* __restrict__ logits, const float* __restrict__ d
   const bool valid = pixr < hw;
   const int pix = valid ? pixr : hw - 1;
   const float* lp = logits + (size_t)b * D * hw + pix;
-  const float* dp = dv_is_vector ? dv : dv + (size_t)b * D * hw + pix;
+  // hypotheses: (D,) vector, (B,D,h,w) tensor, or (dv == null) the ladder first + step*d
+  const float* dp = !dv ? nullptr : dv_is_vector ? dv : dv + (size_t)b * D * hw + pix;
   const size_t dstride = dv_is_vector ? 1 : (size_t)hw;
+  const HypPix hp(hyp, b, D, (size_t)hw, pix);
   float m = 0.f;
   if (!IS_PROB) {
     float lmax = -INFINITY;
@@ -165,7 +167,7 @@ regress_par_kernel(const float* __restrict__ logits, const float* __restrict__ d
   for (int d = s; d < D; d += kK3Lanes) {
     float pr = IS_PROB ? __ldg(lp + (size_t)d * hw) : __fdiv_rn(P[d * 32 + p], denom);
     P[d * 32 + p] = pr;
-    T1[d * 32 + p] = __fmul_rn(pr, __ldg(dp + d * dstride));
+    T1[d * 32 + p] = __fmul_rn(pr, dp ? __ldg(dp + d * dstride) : hp.at(d));
     T2[d * 32 + p] = __fmul_rn(pr, (float)d);
     if (prob && valid) prob[(size_t)b * D * hw + (size_t)d * hw + pix] = pr;
   }
@@ -197,7 +199,7 @@ regress_par_kernel(const float* __restrict__ logits, const float* __restrict__ d
 __global__ void __launch_bounds__(256)
 hypotheses_kernel(const float* __restrict__ cur, int upsample, float half_range, float step,
                   const float* __restrict__ step_dev, float* __restrict__ out, int D, int h,
-                  int w) {
+                  int w, int planes) {
   const int b = blockIdx.y;
   const int pix = blockIdx.x * blockDim.x + threadIdx.x;
   const int hw = h * w;
@@ -227,8 +229,10 @@ hypotheses_kernel(const float* __restrict__ cur, int upsample, float half_range,
     half_range = __fmul_rn((float)D * 0.5f, step);
   }
   const float first = fmaxf(__fsub_rn(c, half_range), 1e-7f);
-  float* op = out + (size_t)b * D * hw + pix;
-  for (int d = 0; d < D; ++d) op[(size_t)d * hw] = __fadd_rn(first, __fmul_rn(step, (float)d));
+  // planes == D: the full (B,D,h,w) ladder; planes == 1: only its first rung (B,h,w) -- the
+  // consumers then generate first + step*d themselves (Hyp, k1_common.cuh)
+  float* op = out + (size_t)b * planes * hw + pix;
+  for (int d = 0; d < planes; ++d) op[(size_t)d * hw] = __fadd_rn(first, __fmul_rn(step, (float)d));
 }
 
 __global__ void __launch_bounds__(256)
@@ -248,11 +252,10 @@ uniform_hypotheses_kernel(float depth_min, float step, const float* __restrict__
 
 using namespace casmvs;
 
-extern "C" int casmvs_regress_fwd(const float* logits, const float* depth_values,
-                                  int dv_is_vector, int input_is_prob, float* depth,
-                                  float* confidence, int64_t* index, float* prob, int B, int D,
-                                  int h, int w, void* stream) {
-  CASMVS_REQUIRE(logits && depth_values && depth && confidence, "regress: null pointer");
+static int regress_impl(const float* logits, const float* depth_values, int dv_is_vector,
+                        const Hyp& hyp, int input_is_prob, float* depth, float* confidence,
+                        int64_t* index, float* prob, int B, int D, int h, int w, void* stream) {
+  CASMVS_REQUIRE(logits && depth && confidence, "regress: null pointer");
   CASMVS_REQUIRE(B >= 0 && B <= 65535 && D > 0 && h > 0 && w > 0, "regress: bad dims");
   if (B == 0) return 0;
   const int hw = h * w;
@@ -269,15 +272,17 @@ extern "C" int casmvs_regress_fwd(const float* logits, const float* depth_values
       static std::atomic<bool> a[kMaxDevices];
       if (int rc = opt_in_smem(regress_par_kernel<true>, 96 * 1024, a, "regress")) return rc;
       regress_par_kernel<true><<<grd, 32 * kK3Lanes, smem, st>>>(
-          logits, depth_values, dv_is_vector, depth, confidence, (long long*)index, prob, D, hw);
+          logits, depth_values, dv_is_vector, hyp, depth, confidence, (long long*)index, prob, D, hw);
     } else {
       static std::atomic<bool> a[kMaxDevices];
       if (int rc = opt_in_smem(regress_par_kernel<false>, 96 * 1024, a, "regress")) return rc;
       regress_par_kernel<false><<<grd, 32 * kK3Lanes, smem, st>>>(
-          logits, depth_values, dv_is_vector, depth, confidence, (long long*)index, prob, D, hw);
+          logits, depth_values, dv_is_vector, hyp, depth, confidence, (long long*)index, prob, D, hw);
     }
     return after_launch("regress");
   }
+  CASMVS_REQUIRE(depth_values, "regress: the ladder form needs the plane-parallel kernel "
+                               "(CASMVS_K3_REG=1, D <= 250)");
   // small maps: narrower blocks so that every SM gets work
   const int threads = (long)hw * B < (long)num_sms() * 4 * kK3Threads ? 32 : kK3Threads;
   dim3 grd((hw + threads - 1) / threads, B);
@@ -290,6 +295,26 @@ extern "C" int casmvs_regress_fwd(const float* logits, const float* depth_values
   return after_launch("regress");
 }
 
+extern "C" int casmvs_regress_fwd(const float* logits, const float* depth_values,
+                                  int dv_is_vector, int input_is_prob, float* depth,
+                                  float* confidence, int64_t* index, float* prob, int B, int D,
+                                  int h, int w, void* stream) {
+  CASMVS_REQUIRE(depth_values, "regress: null pointer");
+  const Hyp hyp{depth_values, nullptr, nullptr, nullptr, 0.f, 0.f};
+  return regress_impl(logits, depth_values, dv_is_vector, hyp, input_is_prob, depth, confidence,
+                      index, prob, B, D, h, w, stream);
+}
+
+// Cascade-internal variant: hypotheses = first + step*d (Hyp, k1_common.cuh), never materialised.
+extern "C" int casmvs_regress_ladder_fwd(const float* logits, const float* first_map,
+                                         const float* first_b, float first, const float* step_b,
+                                         float step, float* depth, float* confidence,
+                                         int64_t* index, int B, int D, int h, int w, void* stream) {
+  const Hyp hyp{nullptr, first_map, first_b, step_b, first, step};
+  return regress_impl(logits, nullptr, 0, hyp, 0, depth, confidence, index, nullptr, B, D, h, w,
+                      stream);
+}
+
 extern "C" int casmvs_depth_hypotheses_fwd(const float* cur, int upsample, float half_range,
                                            float step, const float* step_dev, float* out, int B,
                                            int D, int h, int w, void* stream) {
@@ -300,8 +325,22 @@ extern "C" int casmvs_depth_hypotheses_fwd(const float* cur, int upsample, float
   if (B == 0) return 0;
   dim3 grd((h * w + 255) / 256, B);
   hypotheses_kernel<<<grd, 256, 0, as_stream(stream)>>>(cur, upsample, half_range, step, step_dev,
-                                                        out, D, h, w);
+                                                        out, D, h, w, D);
   return after_launch("depth_hypotheses");
+}
+
+// First rung only: out (B,h,w) = max(cur - half_range, 1e-7), cur optionally upsampled x2.
+extern "C" int casmvs_depth_first_fwd(const float* cur, int upsample, float half_range, float step,
+                                      const float* step_dev, float* out, int B, int D, int h, int w,
+                                      void* stream) {
+  CASMVS_REQUIRE(cur && out, "depth_first: null pointer");
+  CASMVS_REQUIRE(B >= 0 && B <= 65535 && D > 0 && h > 0 && w > 0, "depth_first: bad dims");
+  CASMVS_REQUIRE(!upsample || (h % 2 == 0 && w % 2 == 0), "depth_first: upsample needs even h,w");
+  if (B == 0) return 0;
+  dim3 grd((h * w + 255) / 256, B);
+  hypotheses_kernel<<<grd, 256, 0, as_stream(stream)>>>(cur, upsample, half_range, step, step_dev,
+                                                        out, D, h, w, 1);
+  return after_launch("depth_first");
 }
 
 extern "C" int casmvs_uniform_hypotheses_fwd(float depth_min, float step,

@@ -513,7 +513,7 @@ static int launch_transpose(const float* in, float* out, int N, size_t R, size_t
 int g_k1_dchunk = 0;  // CASMVS_K1_DCHUNK overrides the depth-chunk heuristic
 
 // warp_cost_smem.cu
-int warp_var_smem(const float* feats, const float* proj, const float* dv, float* cost, int B,
+int warp_var_smem(const float* feats, const float* proj, const Hyp& dv, float* cost, int B,
                   int V, int C, int D, int h, int w, int num_groups, int rnd, cudaStream_t st);
 
 template <int NSRC, int CT>
@@ -611,7 +611,8 @@ extern "C" int casmvs_warp_cost_fwd(const float* feats, int feat_layout, const f
   }
   if (nhwc) {
     // TMA-staged generation (warp_cost_smem.cu): 0 = handled, 1 = shape left to the gather kernels
-    const int rc = warp_var_smem(f, proj, depth_values, cost, B, V, C, D, h, w, num_groups, rnd, st);
+    const Hyp hyp{depth_values, nullptr, nullptr, nullptr, 0.f, 0.f};
+    const int rc = warp_var_smem(f, proj, hyp, cost, B, V, C, D, h, w, num_groups, rnd, st);
     if (rc <= 0) return rc;
   }
   if (!gwc && nhwc && (V == 3 || V == 2) && (C == 8 || C == 16 || C == 32) &&
@@ -674,4 +675,28 @@ extern "C" int casmvs_nhwc_to_nchw(const float* in, float* out, int N, int C, si
   CASMVS_REQUIRE(in && out, "nhwc_to_nchw: null pointer");
   // (N,S,C) -> (N,C,S): same kernel with rows = S, cols = C
   return launch_transpose(in, out, N, S, (size_t)C, as_stream(stream), "nhwc_to_nchw");
+}
+
+// Cascade-internal variant of casmvs_warp_cost_fwd: the hypotheses are the ladder
+// first + step*d (see Hyp in k1_common.cuh) instead of a (B,D,h,w) tensor.
+extern "C" int casmvs_warp_cost_ladder_fwd(const float* feats, const float* proj,
+                                           const float* first_map, const float* first_b,
+                                           float first, const float* step_b, float step, float* cost,
+                                           int round_tf32, int B, int V, int C, int D, int h, int w,
+                                           int num_groups, void* stream) {
+  CASMVS_REQUIRE(feats && proj && cost, "warp_cost_ladder: null pointer");
+  CASMVS_REQUIRE(B >= 0 && B <= 65535 && V >= 2 && C > 0 && D > 0 && h >= 2 && w >= 2,
+                 "warp_cost_ladder: bad dims (h,w >= 2)");
+  CASMVS_REQUIRE((size_t)h * w * C < (1u << 31), "warp_cost_ladder: view too large");
+  if (B == 0) return 0;
+  const Hyp hyp{nullptr, first_map, first_b, step_b, first, step};
+  const int rc = warp_var_smem(feats, proj, hyp, cost, B, V, C, D, h, w, num_groups,
+                               round_tf32 ? 1 : 0, as_stream(stream));
+  if (rc == 1) {
+    set_error("warp_cost_ladder: shape not covered by the staged kernel (V-1 in {1,2,4,6}, C in "
+              "{8,16,32}, groups 1 or 8, channels-last features): materialise the hypotheses and "
+              "call casmvs_warp_cost_fwd (got V=%d C=%d G=%d)", V, C, num_groups);
+    return -1;
+  }
+  return rc;
 }

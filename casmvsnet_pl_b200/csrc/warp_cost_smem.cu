@@ -69,7 +69,7 @@ struct Small {            // lives behind the boxes in dynamic shared memory
 template <int NSRC, int C, int TW, int TH, bool REUSE, int MINB, bool GWC = false>
 __global__ void __launch_bounds__(TW* TH*(C / kCPT), MINB)
 warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __restrict__ feats,
-                     const float* __restrict__ proj, const float* __restrict__ dv,
+                     const float* __restrict__ proj, const Hyp hyp,
                      float* __restrict__ cost, int D, int h, int w, int dchunk, int BW, int BH,
                      int box_stride, int tiles_x, int round_tf32) {
   // GWC (group-wise correlation, mvsnet.py:143-144,158-162,170-172) is built for 8 groups:
@@ -117,7 +117,7 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
 
   const int d_begin = blockIdx.z * dchunk;
   const int d_end = min(D, d_begin + dchunk);
-  const float* dvp = dv + (size_t)b * D * hw + pix;
+  const HypPix hp(hyp, b, D, (size_t)hw, pix);
   float* optr = cost + ((size_t)(b * D + d_begin) * hw + pix) * COUT + (GWC ? sub * NG : c0);
   const int row_b = BW * TEXB;
 
@@ -134,8 +134,8 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
       __syncthreads();
       if (tid < NSRC * 4) sm->mm[tid] = (tid & 2) ? INT_MIN : INT_MAX;
       __syncthreads();
-      const float ia = rcp_approx(__ldg(dvp + (size_t)d0 * hw));
-      const float ib = rcp_approx(__ldg(dvp + (size_t)(d0 + n - 1) * hw));
+      const float ia = rcp_approx(hp.at(d0));
+      const float ib = rcp_approx(hp.at(d0 + n - 1));
 #pragma unroll
       for (int v = 0; v < NSRC; ++v) {
         int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
@@ -188,16 +188,14 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
       kx[v] = kMagicBits + bx[v]; ky[v] = kMagicBits + by[v];
       cl[v] = -1;
     }
-    const float* dptr = dvp + (size_t)d0 * hw;
-    float depth_next = __ldg(dptr);
+    float depth_next = hp.at(d0);
     mbar_wait(bar, phase);
     phase ^= 1;
 
     // ---- 3. the planes of this run
     for (int d = d0; d < d0 + n; ++d) {
       const float inv_d = rcp_approx(depth_next);
-      dptr += hw;
-      if (d + 1 < d0 + n) depth_next = __ldg(dptr);
+      if (d + 1 < d0 + n) depth_next = hp.at(d + 1);
       u64 S[4], Q[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -325,7 +323,7 @@ struct Coord { int lbase; float fx, fy; };   // lbase >= 0: window offset in the
 template <int C, int TW, int TH, bool REUSE, int MINB>
 __global__ void __launch_bounds__(TW* TH*(C / kCPT), MINB)
 warp_var_smem_dedup_kernel(const __grid_constant__ CUtensorMap fmap, const float* __restrict__ feats,
-                           const float* __restrict__ proj, const float* __restrict__ dv,
+                           const float* __restrict__ proj, const Hyp hyp,
                            float* __restrict__ cost, int D, int h, int w, int dchunk, int BW, int BH,
                            int box_stride, int tiles_x, int round_tf32) {
   constexpr int NSRC = 2, V = 3, TPP = C / kCPT, TEXB = C * 4, NT = TW * TH * TPP;
@@ -367,7 +365,7 @@ warp_var_smem_dedup_kernel(const __grid_constant__ CUtensorMap fmap, const float
   const u64 inv_v2 = pk2(inv_v, inv_v), ninv_v2 = pk2(-inv_v, -inv_v);
   const int d_begin = blockIdx.z * dchunk;
   const int d_end = min(D, d_begin + dchunk);
-  const float* dvp = dv + (size_t)b * D * hw + pix;
+  const HypPix hp(hyp, b, D, (size_t)hw, pix);
   float* optr = cost + ((size_t)(b * D + d_begin) * hw + pix) * C + c0;
   const int row_b = BW * TEXB;
   Tex8 t00[NSRC], t01[NSRC], t10[NSRC], t11[NSRC];
@@ -383,8 +381,8 @@ warp_var_smem_dedup_kernel(const __grid_constant__ CUtensorMap fmap, const float
       __syncthreads();
       // footprint: each thread handles its own view (both views are covered by sub 0 / 1)
       {
-        const float ia = rcp_approx(__ldg(dvp + (size_t)d0 * hw));
-        const float ib = rcp_approx(__ldg(dvp + (size_t)(d0 + n - 1) * hw));
+        const float ia = rcp_approx(hp.at(d0));
+        const float ib = rcp_approx(hp.at(d0 + n - 1));
         int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -443,7 +441,7 @@ warp_var_smem_dedup_kernel(const __grid_constant__ CUtensorMap fmap, const float
     for (int d = d0; d < d0 + n; d += PPS) {
       // this thread's (plane, view): plane d + mpo (clamped: an odd tail computes a dummy)
       const int dm = min(d + mpo, d0 + n - 1);
-      const float inv_d = rcp_approx(__ldg(dvp + (size_t)dm * hw));
+      const float inv_d = rcp_approx(hp.at(dm));
       Coord mine;
       {
         const float qx = fmaf(mtx, inv_d, max_), qy = fmaf(mty, inv_d, may_);
@@ -498,7 +496,7 @@ warp_var_smem_dedup_kernel(const __grid_constant__ CUtensorMap fmap, const float
           } else {
             // robust gather path: re-evaluate the sample from the projection (rare)
             const float* P = sm->proj + v * 12;
-            const float id = rcp_approx(__ldg(dvp + (size_t)dd * hw));
+            const float id = rcp_approx(hp.at(dd));
             const float qx = fmaf(P[3], id, fmaf(P[0], xf, fmaf(P[1], yf, P[2])));
             const float qy = fmaf(P[7], id, fmaf(P[4], xf, fmaf(P[5], yf, P[6])));
             const float qz = fmaf(P[11], id, fmaf(P[8], xf, fmaf(P[9], yf, P[10])));
@@ -578,7 +576,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 template <int NSRC, int C, int TW, int TH, bool REUSE, int MINB, bool GWC = false>
-static int launch(const float* feats, const float* proj, const float* dv, float* cost, int B, int D,
+static int launch(const float* feats, const float* proj, const Hyp& dv, float* cost, int B, int D,
                   int h, int w, int rnd, cudaStream_t st) {
   constexpr int NT = TW * TH * (C / kCPT);
   // box = tile + margins: sweep of the depth run + scale/rotation of the view + the 2x2 window
@@ -608,7 +606,7 @@ static int launch(const float* feats, const float* proj, const float* dv, float*
 }
 
 template <int C, int TW, int TH, bool REUSE, int MINB>
-static int launch_dedup(const float* feats, const float* proj, const float* dv, float* cost, int B,
+static int launch_dedup(const float* feats, const float* proj, const Hyp& dv, float* cost, int B,
                         int D, int h, int w, int rnd, cudaStream_t st) {
   constexpr int NSRC = 2, NT = TW * TH * (C / kCPT);
   static const int mx = env_int("CASMVS_K1_MARGIN_X", 16);
@@ -638,7 +636,7 @@ static int launch_dedup(const float* feats, const float* proj, const float* dv, 
 
 // Variance cost volume, channels-last features and output.  Returns 0 when handled, 1 when the
 // shape is left to the gather kernels of warp_cost.cu, <0 on error.
-int warp_var_smem(const float* feats, const float* proj, const float* dv, float* cost, int B,
+int warp_var_smem(const float* feats, const float* proj, const Hyp& dv, float* cost, int B,
                   int V, int C, int D, int h, int w, int num_groups, int rnd, cudaStream_t st) {
   static const int enabled = k1s::env_int("CASMVS_K1_SMEM", 1);
   if (!enabled) return 1;

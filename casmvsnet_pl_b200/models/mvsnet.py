@@ -360,6 +360,10 @@ class CascadeMVSNet(nn.Module):
         # confidence gather uses; the reference keeps them internal
         self.return_index = False
         self._last_index = None
+        # cascade-internal fusion: K4 writes only the first rung of each stage's hypothesis ladder
+        # and K1 / K3 generate first + step*d themselves (bit-identical results; the (B,D,h,w)
+        # hypothesis tensor is neither written nor read).  CASMVS_LADDER=0 turns it off.
+        self.fuse_hypotheses = os.environ.get("CASMVS_LADDER", "1") != "0"
         for l in range(self.levels):
             cin = self.G if self.G > 1 else 8 * 2 ** l
             setattr(self, f"cost_reg_{l}", CostRegNet(cin, norm_act))
@@ -458,14 +462,26 @@ class CascadeMVSNet(nn.Module):
                 depth_interval_l = depth_interval * self.interval_ratios[l]
                 D = self.n_depths[l]
                 h, w = feats_l.shape[-2:]
-                if l == self.levels - 1:
-                    depth_values = ops.uniform_hypotheses(init_depth_min, depth_interval_l, D,
-                                                          B, h, w, imgs.device)
+                cost_reg = getattr(self, f"cost_reg_{l}")
+                if self.fuse_hypotheses and ops.ladder_supported(V, feats_l.shape[2], self.G):
+                    first = init_depth_min if l == self.levels - 1 else \
+                        ops.depth_first(depth_l, D, depth_interval_l)
+                    lad = ops.Ladder(first, depth_interval_l, D, B, h, w, imgs.device)
+                    cost = ops.warp_cost_ladder(feats_l, proj_mats_l, lad, self.G,
+                                                round_tf32=(cost_reg.precision == "tf32"))
+                    logits = cost_reg(cost).squeeze(1)
+                    del cost
+                    depth_l, confidence_l, self._last_index = ops.regress_ladder(
+                        logits, lad, want_index=self.return_index)
                 else:
-                    depth_values = ops.depth_hypotheses(depth_l, D, depth_interval_l,
-                                                        upsample=True)
-                depth_l, confidence_l = self.predict_depth(
-                    feats_l, proj_mats_l, depth_values, getattr(self, f"cost_reg_{l}"))
+                    if l == self.levels - 1:
+                        depth_values = ops.uniform_hypotheses(init_depth_min, depth_interval_l, D,
+                                                              B, h, w, imgs.device)
+                    else:
+                        depth_values = ops.depth_hypotheses(depth_l, D, depth_interval_l,
+                                                            upsample=True)
+                    depth_l, confidence_l = self.predict_depth(
+                        feats_l, proj_mats_l, depth_values, cost_reg)
                 results[f"depth_{l}"] = depth_l
                 results[f"confidence_{l}"] = confidence_l
                 if self.return_index:

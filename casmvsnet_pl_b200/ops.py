@@ -316,6 +316,92 @@ def _uniform_hypotheses(init_depth_min, depth_interval, n_depths, B, h, w, devic
     return out
 
 
+# --------------------------------------------------------------------------- ladder forms
+class Ladder:
+    """Hypotheses first + step*d of one cascade stage, never materialised as (B,D,h,w):
+    `first` is a (B,h,w) tensor [per-pixel], a (B,) tensor [per batch item] or a float; `step` a
+    (B,) tensor or a float; D planes.  `materialize()` gives the tensor the public API takes."""
+
+    def __init__(self, first, step, D, B, h, w, device):
+        self.first, self.step, self.D, self.B, self.h, self.w, self.device = first, step, D, B, h, w, device
+
+    def _args(self):
+        fm = fb = sb = None
+        f = s = 0.0
+        if torch.is_tensor(self.first):
+            if self.first.dim() == 3:
+                fm = self.first.contiguous()
+            else:
+                fb = self.first.reshape(-1).contiguous()
+        else:
+            f = float(self.first)
+        if torch.is_tensor(self.step):
+            sb = self.step.reshape(-1).contiguous()
+        else:
+            s = float(self.step)
+        return fm, fb, f, sb, s
+
+    def materialize(self):
+        d = torch.arange(self.D, device=self.device, dtype=torch.float32).view(1, -1, 1, 1)
+        first = self.first if torch.is_tensor(self.first) else torch.tensor(float(self.first), device=self.device)
+        step = self.step if torch.is_tensor(self.step) else torch.tensor(float(self.step), device=self.device)
+        first = first.view(self.B, 1, self.h, self.w) if first.dim() == 3 else first.reshape(-1, 1, 1, 1)
+        return (first + step.reshape(-1, 1, 1, 1) * d).expand(self.B, self.D, self.h, self.w).contiguous()
+
+
+def ladder_supported(V, C, num_groups):
+    """Shapes the staged K1 kernel (the only one that takes a ladder) covers."""
+    return (V - 1) in (1, 2, 4, 6) and C in (8, 16, 32) and num_groups in (1, 8)
+
+
+@_on_tensor_device
+def warp_cost_ladder(feats, proj_mats, ladder, num_groups=1, round_tf32=False):
+    """warp_cost with the hypotheses given as a Ladder; feats must be channels-last."""
+    _require_cuda(feats, proj_mats)
+    _no_grad_only(feats)
+    B, V, C, h, w = feats.shape
+    assert is_channels_last_feats(feats) and (ladder.B, ladder.h, ladder.w) == (B, h, w)
+    cout = C if num_groups == 1 else num_groups
+    out = torch.empty(B, ladder.D, h, w, cout, device=feats.device, dtype=torch.float32)
+    fm, fb, f, sb, s = ladder._args()
+    check(_lib.load().casmvs_warp_cost_ladder_fwd(_ptr(feats), _ptr(proj_mats.contiguous()), _ptr(fm),
+                                                  _ptr(fb), f, _ptr(sb), s, _ptr(out),
+                                                  1 if round_tf32 else 0, B, V, C, ladder.D, h, w,
+                                                  num_groups, _stream()), "warp_cost_ladder")
+    return as_volume_view(out)
+
+
+@_on_tensor_device
+def regress_ladder(logits, ladder, want_index=False):
+    _require_cuda(logits)
+    _no_grad_only(logits)
+    lg = logits.contiguous()
+    B, D, h, w = lg.shape
+    depth = torch.empty(B, h, w, device=lg.device, dtype=torch.float32)
+    conf = torch.empty_like(depth)
+    index = torch.empty(B, h, w, device=lg.device, dtype=torch.int64) if want_index else None
+    fm, fb, f, sb, s = ladder._args()
+    check(_lib.load().casmvs_regress_ladder_fwd(_ptr(lg), _ptr(fm), _ptr(fb), f, _ptr(sb), s,
+                                                _ptr(depth), _ptr(conf), _ptr(index), B, D, h, w,
+                                                _stream()), "regress_ladder")
+    return depth, conf, index
+
+
+@_on_tensor_device
+def depth_first(current_depth, n_depths, depth_interval):
+    """First rung of depth_hypotheses(upsample=True): (B,h/2,w/2) -> (B,h,w)."""
+    _require_cuda(current_depth)
+    cur = current_depth.contiguous()
+    B, hi, wi = cur.shape
+    h, w = 2 * hi, 2 * wi
+    step, step_dev = _interval_args(depth_interval, B, cur.device)
+    half = float(n_depths / 2 * step)
+    out = torch.empty(B, h, w, device=cur.device, dtype=torch.float32)
+    check(_lib.load().casmvs_depth_first_fwd(_ptr(cur), 1, half, step, _ptr(step_dev), _ptr(out), B,
+                                             n_depths, h, w, _stream()), "depth_first")
+    return out
+
+
 # --------------------------------------------------------------------------- FPN (adjacent)
 @_on_tensor_device
 def fpn_level(prev, c, lat_w, lat_b, smooth_w, smooth_b, want_feat):

@@ -185,6 +185,28 @@ int casmvs_uniform_hypotheses_fwd(float depth_min, float step, const float* dept
                                   const float* step_dev, float* out,
                                   int B, int D, int h, int w, void* stream);
 
+/* ---- cascade-internal forms: hypotheses as a ladder, never materialised -----------------
+ * Inside the cascade every pixel's hypotheses are first + step*d (get_depth_values,
+ * models/modules.py:44-48; initial planes, models/mvsnet.py:215-229).  These entries take the
+ * ladder instead of the (B,D,h,w) tensor and generate it in the kernel with the same two
+ * roundings, so K4's D*h*w floats are neither written nor read back by K1 and K3 (bit-identical
+ * results).  first: `first_map` (B,h,w) per pixel, else `first_b` (B) per batch item, else the
+ * scalar `first`; step: `step_b` (B) else the scalar `step`.
+ * casmvs_depth_first_fwd writes only the first rung (B,h,w) of casmvs_depth_hypotheses_fwd.
+ * casmvs_warp_cost_ladder_fwd: channels-last features and cost volume; shapes of the staged
+ * kernel only (V-1 in {1,2,4,6}, C in {8,16,32}, num_groups 1 or 8), error otherwise. */
+int casmvs_depth_first_fwd(const float* cur, int upsample, float half_range, float step,
+                           const float* step_dev, float* out, int B, int D, int h, int w,
+                           void* stream);
+int casmvs_warp_cost_ladder_fwd(const float* feats, const float* proj, const float* first_map,
+                                const float* first_b, float first, const float* step_b, float step,
+                                float* cost, int round_tf32, int B, int V, int C, int D, int h, int w,
+                                int num_groups, void* stream);
+int casmvs_regress_ladder_fwd(const float* logits, const float* first_map, const float* first_b,
+                              float first, const float* step_b, float step, float* depth,
+                              float* confidence, int64_t* index, int B, int D, int h, int w,
+                              void* stream);
+
 /* ---- FeatureNet top-down path, fused (adjacent to the hot path) ----
  * One pyramid level of models/mvsnet.py:36-52:
  *   feat = upsample_x2_bilinear(prev, align_corners=True) + conv1x1(c, lat_w) + lat_b   (32 ch)

@@ -292,3 +292,26 @@ def test_weight_image_lifetime_and_graph_generation():
     assert _lib.weight_cache_generation() > gen
     with pytest.raises(_lib.CasMVSError):
         g()
+
+
+@pytest.mark.parametrize("G", [1, 8])
+def test_ladder_fusion_is_bit_identical(G):
+    """Generating the hypothesis ladder inside K1 / K3 (fuse_hypotheses) gives exactly the
+    outputs of the path that materialises (B,D,h,w) hypotheses through K4, for float and
+    tensor-valued depth parameters."""
+    model, _ = build(G, "tf32")
+    imgs, pm, dmin, dint = synth.make_inputs(B=2, V=3, W=160, H=128, seed=2)
+    imgs, pm = imgs.to(DEV), pm.to(DEV)
+    tparams = (torch.tensor([[425.0], [431.5]], device=DEV), torch.tensor([[2.65], [2.5]], device=DEV))
+    for a, b in ((dmin, dint), tparams):
+        model.fuse_hypotheses = True
+        model.return_index = True
+        fused = {k: v.clone() for k, v in model(imgs, pm, a, b).items()}
+        model.fuse_hypotheses = False
+        plain = model(imgs, pm, a, b)
+        for k in plain:
+            assert torch.equal(fused[k], plain[k]), k
+    # the Ladder helper itself reproduces K4's tensors bit for bit
+    cur = plain["depth_1"]
+    lad = ops.Ladder(ops.depth_first(cur, 8, 2.65), 2.65, 8, 2, 128, 160, DEV)
+    assert torch.equal(lad.materialize(), ops.depth_hypotheses(cur, 8, 2.65, upsample=True))
