@@ -23,8 +23,9 @@ normalize_u8_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, siz
   const size_t n = blockIdx.y;
   const uint8_t* ip = in + n * hw * 3;
   float* op = out + n * hw * 3;
-  // 4 pixels (12 bytes = 3 words) per thread per step; hw % 4 tail handled scalar
-  const size_t quads = hw / 4;
+  // 4 pixels (12 bytes = 3 words) per thread per step when the planes of every image stay
+  // 16 B aligned (hw % 4 == 0); otherwise (N == 1, odd sizes) the scalar path does everything
+  const size_t quads = (hw % 4 == 0) ? hw / 4 : 0;
   for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads;
        q += (size_t)gridDim.x * blockDim.x) {
     const uint32_t* wp = reinterpret_cast<const uint32_t*>(ip + q * 12);

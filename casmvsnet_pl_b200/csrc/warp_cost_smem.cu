@@ -654,7 +654,7 @@ int warp_var_smem(const float* feats, const float* proj, const Hyp& dv, float* c
   }
   // tile / register-budget variants (CASMVS_K1S_VARIANT; defaults measured on cfg2, see
   // profiles/r2_k1_variants.jsonl): {tile, REUSE windows in registers, min resident CTAs}
-  static const int variant = env_int("CASMVS_K1S_VARIANT", 0);
+  static const int variant = env_int("CASMVS_K1S_VARIANT", 4);
 #define K1S(VAR, NS, CC, TW_, TH_, RU, MB) \
   if (variant == VAR && V - 1 == NS && C == CC) return launch<NS, CC, TW_, TH_, RU, MB>(feats, proj, dv, cost, B, D, h, w, rnd, st);
   K1S(0, 2, 8, 32, 4, true, 4) K1S(0, 2, 16, 32, 4, true, 2) K1S(0, 2, 32, 16, 4, true, 2)
