@@ -64,17 +64,41 @@ struct Small {            // lives behind the boxes in dynamic shared memory
   unsigned long long bar;
 };
 
+// CP channels per thread (8 or 16).  16 halves the per-output share of everything that is per
+// (pixel, plane, view) -- homography, reciprocal, floor, window address, swizzle, predicates:
+// ~60 % of the instruction stream at CP = 8 -- at the price of a 64-register window.
+template <int CP> struct TexP { u64 v[CP / 2]; };
+template <int CP>
+__device__ __forceinline__ void lds_texp(uint32_t addr, TexP<CP>& t) {   // CP*4 bytes, 16 B chunks
+#pragma unroll
+  for (int k = 0; k < CP / 4; ++k)
+    asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(t.v[2 * k]), "=l"(t.v[2 * k + 1])
+                 : "r"(addr ^ (16u * k)));
+}
+template <int CP>
+__device__ __forceinline__ TexP<CP> ldg_texp(const float* p) {
+  TexP<CP> t;
+#pragma unroll
+  for (int k = 0; k < CP / 8; ++k) {
+    const Tex8 a = ldg256(p + 8 * k);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t.v[4 * k + j] = a.v[j];
+  }
+  return t;
+}
+
 // NSRC source views, C channels (8 per thread), TW x TH pixel tile; REUSE: keep the 2x2 windows
 // in registers across planes (64 registers at NSRC = 2).
-template <int NSRC, int C, int TW, int TH, bool REUSE, int MINB, bool GWC = false>
-__global__ void __launch_bounds__(TW* TH*(C / kCPT), MINB)
+template <int NSRC, int C, int TW, int TH, bool REUSE, int MINB, bool GWC = false, int CP = 8>
+__global__ void __launch_bounds__(TW* TH*(C / CP), MINB)
 warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __restrict__ feats,
                      const float* __restrict__ proj, const Hyp hyp,
                      float* __restrict__ cost, int D, int h, int w, int dchunk, int BW, int BH,
                      int box_stride, int tiles_x, int round_tf32) {
   // GWC (group-wise correlation, mvsnet.py:143-144,158-162,170-172) is built for 8 groups:
   // C/8 in {1,2,4} channels per group, every thread owns 8/(C/8) whole groups
-  constexpr int V = NSRC + 1, TPP = C / kCPT, TEXB = C * 4, NT = TW * TH * TPP;
+  constexpr int V = NSRC + 1, TPP = C / CP, TEXB = C * 4, NT = TW * TH * TPP, NP = CP / 2;
+  static_assert(!GWC || CP == 8, "group-wise correlation is built for 8 channels per thread");
   constexpr int CPG = C / 8, NG = kCPT / CPG, COUT = GWC ? 8 : C;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -89,7 +113,7 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
   const int xr = tile_x * TW + px, yr = tile_y * TH + py;
   const bool active = xr < w && yr < h;
   const int x = min(xr, w - 1), y = min(yr, h - 1);
-  const int c0 = sub * kCPT;
+  const int c0 = sub * CP;
   const int hw = h * w, pix = y * w + x;
 
   for (int i = tid; i < NSRC * 12; i += NT) sm->proj[i] = proj[(size_t)b * NSRC * 12 + i];
@@ -111,7 +135,7 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
   }
   const size_t view_stride = (size_t)hw * C;
   const float* fb = feats + (size_t)b * V * view_stride + c0;
-  const Tex8 ref = ldg256(fb + (size_t)pix * C);
+  const TexP<CP> ref = ldg_texp<CP>(fb + (size_t)pix * C);
   const float inv_v = 1.f / (float)V;
   const u64 inv_v2 = pk2(inv_v, inv_v), ninv_v2 = pk2(-inv_v, -inv_v);
 
@@ -121,7 +145,7 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
   float* optr = cost + ((size_t)(b * D + d_begin) * hw + pix) * COUT + (GWC ? sub * NG : c0);
   const int row_b = BW * TEXB;
 
-  Tex8 t00[NSRC], t01[NSRC], t10[NSRC], t11[NSRC];
+  TexP<CP> t00[NSRC], t01[NSRC], t10[NSRC], t11[NSRC];
   int cl[NSRC];
   uint32_t phase = 0;
 
@@ -196,9 +220,9 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
     for (int d = d0; d < d0 + n; ++d) {
       const float inv_d = rcp_approx(depth_next);
       if (d + 1 < d0 + n) depth_next = hp.at(d + 1);
-      u64 S[4], Q[4];
+      u64 S[NP], Q[NP];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < NP; ++k) {
         S[k] = GWC ? 0ull : ref.v[k];            // gwc: the reference is NOT in the sum (:144)
         Q[k] = mul2(ref.v[k], ref.v[k]);
       }
@@ -214,23 +238,23 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
         const int xi = __float_as_int(fu) - kx[v], yi = __float_as_int(fv) - ky[v];
         const bool inbox = (unsigned)xi < (unsigned)(BW - 1) && (unsigned)yi < (unsigned)(BH - 1) &&
                            qz > 1e-7f;
-        u64 r[4];
+        u64 r[NP];
         if (__builtin_expect(inbox, 1)) {
           const float fx = u - (fu - kMagic), fy = vv - (fv - kMagic);
           const float wxa = 1.f - fx, wya = 1.f - fy;
           const int l00 = v * box_stride + yi * row_b + xi * TEXB + c0 * 4;
           if (!REUSE || l00 != cl[v]) {
-            lds_tex(base + swz<TEXB>(l00), t00[v]);
-            lds_tex(base + swz<TEXB>(l00 + TEXB), t01[v]);
-            lds_tex(base + swz<TEXB>(l00 + row_b), t10[v]);
-            lds_tex(base + swz<TEXB>(l00 + row_b + TEXB), t11[v]);
+            lds_texp<CP>(base + swz<TEXB>(l00), t00[v]);
+            lds_texp<CP>(base + swz<TEXB>(l00 + TEXB), t01[v]);
+            lds_texp<CP>(base + swz<TEXB>(l00 + row_b), t10[v]);
+            lds_texp<CP>(base + swz<TEXB>(l00 + row_b + TEXB), t11[v]);
             cl[v] = l00;
           }
           const float w00 = wxa * wya, w01 = fx * wya, w10 = wxa * fy, w11 = fx * fy;
           const u64 p00 = pk2(w00, w00), p01 = pk2(w01, w01), p10 = pk2(w10, w10),
                     p11 = pk2(w11, w11);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < NP; ++k) {
             // tap order nw, ne, sw, se like ATen grid_sampler_2d
             u64 a = mul2(t00[v].v[k], p00);
             a = fma2(t01[v].v[k], p01, a);
@@ -243,22 +267,25 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
           continue;
         } else {
           // robust gather path for a window outside the staged box (NaN propagates like ATen)
-          Window win;
-          float w00, w01, w10, w11;
-          sample_view<C>(fb + (size_t)(v + 1) * view_stride, qx, qy, qz, h, w, C, w * C, win, w00,
-                         w01, w10, w11);
-          const u64 p00 = pk2(w00, w00), p01 = pk2(w01, w01), p10 = pk2(w10, w10),
-                    p11 = pk2(w11, w11);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            u64 a = mul2(win.t00.v[k], p00);
-            a = fma2(win.t01.v[k], p01, a);
-            a = fma2(win.t10.v[k], p10, a);
-            r[k] = fma2(win.t11.v[k], p11, a);
+          for (int hh = 0; hh < CP / 8; ++hh) {
+            Window win;
+            float w00, w01, w10, w11;
+            sample_view<C>(fb + (size_t)(v + 1) * view_stride + 8 * hh, qx, qy, qz, h, w, C, w * C,
+                           win, w00, w01, w10, w11);
+            const u64 p00 = pk2(w00, w00), p01 = pk2(w01, w01), p10 = pk2(w10, w10),
+                      p11 = pk2(w11, w11);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              u64 a = mul2(win.t00.v[k], p00);
+              a = fma2(win.t01.v[k], p01, a);
+              a = fma2(win.t10.v[k], p10, a);
+              r[4 * hh + k] = fma2(win.t11.v[k], p11, a);
+            }
           }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < NP; ++k) {
           S[k] = add2(S[k], r[k]);
           if (!GWC) Q[k] = fma2(r[k], r[k], Q[k]);
         }
@@ -267,7 +294,7 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
         // cost[g] = mean_{c in g}(S_c * ref_c) / (V-1)     (mvsnet.py:170-172)
         float pr[kCPT], o[NG];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) unpk2(mul2(S[k], ref.v[k]), pr[2 * k], pr[2 * k + 1]);
+        for (int k = 0; k < NP; ++k) unpk2(mul2(S[k], ref.v[k]), pr[2 * k], pr[2 * k + 1]);
 #pragma unroll
         for (int k = 0; k < NG; ++k) {
           float acc = CPG == 1 ? pr[k] : CPG == 2 ? pr[2 * k] + pr[2 * k + 1]
@@ -289,21 +316,27 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
         continue;
       }
       // var = Q/V - (S/V)^2   (mvsnet.py:166-168)
-      u64 o[4];
+      u64 o[NP];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < NP; ++k) {
         const u64 m = mul2(S[k], inv_v2), mn = mul2(S[k], ninv_v2);
         o[k] = fma2(mn, m, mul2(Q[k], inv_v2));
       }
       if (round_tf32) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < NP; ++k) {
           float lo, hi;
           unpk2(o[k], lo, hi);
           o[k] = pk2(round_tf32_f(lo), round_tf32_f(hi));
         }
       }
-      if (active) stg256(optr, o);
+      if (active) {
+#pragma unroll
+        for (int hh = 0; hh < CP / 8; ++hh) {
+          const u64 oo[4] = {o[4 * hh], o[4 * hh + 1], o[4 * hh + 2], o[4 * hh + 3]};
+          stg256(optr + 8 * hh, oo);
+        }
+      }
       optr += (size_t)hw * C;
     }
     d0 += n;
@@ -542,6 +575,215 @@ warp_var_smem_dedup_kernel(const __grid_constant__ CUtensorMap fmap, const float
   }
 }
 
+// ---- plane-group variant: window reuse WITHOUT persistent registers -----------------------------
+// ncu on the kernel above (profiles/r2_k1_variants.txt): the LSU data pipe sits at 62-74 % of its
+// peak (the gather kernel: 66-72 %) -- both generations are bound by the 32 B of tap traffic per
+// output float, not by latency.  Keeping the 2x2 windows of both views in registers across
+// planes (REUSE) cuts the shared-memory wavefronts by 38 % but needs 166 registers (or spills,
+// whose local-memory traffic goes through the same LSU pipe).  Here a thread walks PG planes
+// of ONE view before turning to the next view: the window lives only inside that short walk
+// (32 registers, re-loaded only when it moves: ~0.43 texel per plane in the cascade), and what
+// persists between the views is one blended value per (plane, channel) -- 8 registers per plane.
+// 2 source views, variance cost.  out = (ref^2 + r1^2 + r2^2)/3 - ((ref + r1 + r2)/3)^2, summed
+// in the order of the kernel above (bit-identical).
+template <int C, int TW, int TH, int PG, int MINB>
+__global__ void __launch_bounds__(TW* TH*(C / kCPT), MINB)
+warp_var_smem_pg_kernel(const __grid_constant__ CUtensorMap fmap, const float* __restrict__ feats,
+                        const float* __restrict__ proj, const Hyp hyp, float* __restrict__ cost,
+                        int D, int h, int w, int dchunk, int BW, int BH, int box_stride, int tiles_x,
+                        int round_tf32) {
+  constexpr int NSRC = 2, V = 3, TPP = C / kCPT, TEXB = C * 4, NT = TW * TH * TPP;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  Small* sm = reinterpret_cast<Small*>(smem_raw + (base - smem_u32(smem_raw)) + NSRC * box_stride);
+  const uint32_t bar = smem_u32(&sm->bar);
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
+  const int lp = tid / TPP, sub = tid - lp * TPP;
+  const int py = lp / TW, px = lp - py * TW;
+  const int xr = tile_x * TW + px, yr = tile_y * TH + py;
+  const bool active = xr < w && yr < h;
+  const int x = min(xr, w - 1), y = min(yr, h - 1);
+  const int c0 = sub * kCPT;
+  const int hw = h * w, pix = y * w + x;
+
+  for (int i = tid; i < NSRC * 12; i += NT) sm->proj[i] = proj[(size_t)b * NSRC * 12 + i];
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const float xf = (float)x, yf = (float)y;
+  float ax[NSRC], ay[NSRC], az[NSRC], tx[NSRC], ty[NSRC], tz[NSRC];
+#pragma unroll
+  for (int v = 0; v < NSRC; ++v) {
+    const float* P = sm->proj + v * 12;
+    ax[v] = fmaf(P[0], xf, fmaf(P[1], yf, P[2]));
+    ay[v] = fmaf(P[4], xf, fmaf(P[5], yf, P[6]));
+    az[v] = fmaf(P[8], xf, fmaf(P[9], yf, P[10]));
+    tx[v] = P[3]; ty[v] = P[7]; tz[v] = P[11];
+  }
+  const size_t view_stride = (size_t)hw * C;
+  const float* fb = feats + (size_t)b * V * view_stride + c0;
+  const Tex8 ref = ldg256(fb + (size_t)pix * C);
+  const float inv_v = 1.f / (float)V;
+  const u64 inv_v2 = pk2(inv_v, inv_v), ninv_v2 = pk2(-inv_v, -inv_v);
+  const int d_begin = blockIdx.z * dchunk;
+  const int d_end = min(D, d_begin + dchunk);
+  const HypPix hp(hyp, b, D, (size_t)hw, pix);
+  float* optr = cost + ((size_t)(b * D + d_begin) * hw + pix) * C + c0;
+  const int row_b = BW * TEXB;
+  uint32_t phase = 0;
+
+  for (int d0 = d_begin; d0 < d_end;) {
+    int n = d_end - d0;
+    int bx[NSRC], by[NSRC];
+    for (;;) {
+      __syncthreads();
+      if (tid < NSRC * 4) sm->mm[tid] = (tid & 2) ? INT_MIN : INT_MAX;
+      __syncthreads();
+      const float ia = rcp_approx(hp.at(d0));
+      const float ib = rcp_approx(hp.at(d0 + n - 1));
+#pragma unroll
+      for (int v = 0; v < NSRC; ++v) {
+        int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float id = e ? ib : ia;
+          const float qz = fmaf(tz[v], id, az[v]);
+          const float rz = rcp_approx(qz);
+          const float u = fmaf(tx[v], id, ax[v]) * rz, vv = fmaf(ty[v], id, ay[v]) * rz;
+          if (active && qz > 1e-7f && u > -2.f && u < (float)(w + 1) && vv > -2.f &&
+              vv < (float)(h + 1)) {
+            const int xi = __float2int_rd(u), yi = __float2int_rd(vv);
+            mnx = min(mnx, xi); mxx = max(mxx, xi);
+            mny = min(mny, yi); mxy = max(mxy, yi);
+          }
+        }
+        mnx = __reduce_min_sync(0xffffffffu, mnx); mny = __reduce_min_sync(0xffffffffu, mny);
+        mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
+        if ((tid & 31) == 0) {
+          atomicMin(&sm->mm[v * 4 + 0], mnx); atomicMin(&sm->mm[v * 4 + 1], mny);
+          atomicMax(&sm->mm[v * 4 + 2], mxx); atomicMax(&sm->mm[v * 4 + 3], mxy);
+        }
+      }
+      __syncthreads();
+      bool fits = true;
+#pragma unroll
+      for (int v = 0; v < NSRC; ++v) {
+        const int mnx = sm->mm[v * 4 + 0], mny = sm->mm[v * 4 + 1];
+        const int mxx = sm->mm[v * 4 + 2], mxy = sm->mm[v * 4 + 3];
+        if (mnx > mxx) { bx[v] = 0; by[v] = 0; continue; }
+        const int sx = mxx + 2 - mnx, sy = mxy + 2 - mny;
+        if (sx > BW || sy > BH) fits = false;
+        bx[v] = mnx - max(0, (BW - sx) >> 1);
+        by[v] = mny - max(0, (BH - sy) >> 1);
+      }
+      if (fits || n == 1) break;
+      n = (n + 1) >> 1;
+    }
+    if (tid == 0) {
+      tma::mbar_expect_tx(bar, (uint32_t)(NSRC * BW * BH * TEXB));
+#pragma unroll
+      for (int v = 0; v < NSRC; ++v)
+        tma::tma_load_4d(base + v * box_stride, &fmap, bar, 0, bx[v], by[v], b * V + v + 1);
+    }
+    int kx[NSRC], ky[NSRC];
+#pragma unroll
+    for (int v = 0; v < NSRC; ++v) { kx[v] = kMagicBits + bx[v]; ky[v] = kMagicBits + by[v]; }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+
+    for (int d = d0; d < d0 + n; d += PG) {
+      float inv_d[PG];
+#pragma unroll
+      for (int p = 0; p < PG; ++p) inv_d[p] = rcp_approx(hp.at(min(d + p, d0 + n - 1)));
+      u64 r1[PG][4];
+#pragma unroll
+      for (int v = 0; v < NSRC; ++v) {
+        Tex8 t00, t01, t10, t11;
+        int cur = -1;                                   // window held in t00..t11
+#pragma unroll
+        for (int p = 0; p < PG; ++p) {
+          const float qx = fmaf(tx[v], inv_d[p], ax[v]);
+          const float qy = fmaf(ty[v], inv_d[p], ay[v]);
+          const float qz = fmaf(tz[v], inv_d[p], az[v]);
+          const float rz = rcp_approx(qz);
+          const float u = qx * rz, vv = qy * rz;
+          const float fu = fadd_rd(u, kMagic), fv = fadd_rd(vv, kMagic);
+          const int xi = __float_as_int(fu) - kx[v], yi = __float_as_int(fv) - ky[v];
+          const bool inbox = (unsigned)xi < (unsigned)(BW - 1) && (unsigned)yi < (unsigned)(BH - 1) &&
+                             qz > 1e-7f;
+          u64 r[4] = {0ull, 0ull, 0ull, 0ull};          // packed +0.f: a sample that is exactly zero
+          if (__builtin_expect(inbox, 1)) {
+            const float fx = u - (fu - kMagic), fy = vv - (fv - kMagic);
+            const float wxa = 1.f - fx, wya = 1.f - fy;
+            const int l00 = v * box_stride + yi * row_b + xi * TEXB + c0 * 4;
+            if (l00 != cur) {
+              lds_tex(base + swz<TEXB>(l00), t00);
+              lds_tex(base + swz<TEXB>(l00 + TEXB), t01);
+              lds_tex(base + swz<TEXB>(l00 + row_b), t10);
+              lds_tex(base + swz<TEXB>(l00 + row_b + TEXB), t11);
+              cur = l00;
+            }
+            const float w00 = wxa * wya, w01 = fx * wya, w10 = wxa * fy, w11 = fx * fy;
+            const u64 p00 = pk2(w00, w00), p01 = pk2(w01, w01), p10 = pk2(w10, w10),
+                      p11 = pk2(w11, w11);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              u64 a = mul2(t00.v[k], p00);
+              a = fma2(t01.v[k], p01, a);
+              a = fma2(t10.v[k], p10, a);
+              r[k] = fma2(t11.v[k], p11, a);
+            }
+          } else if (!(qz <= 1e-7f || u <= -1.f || u >= (float)w || vv <= -1.f || vv >= (float)h)) {
+            Window win;
+            float w00, w01, w10, w11;
+            sample_view<C>(fb + (size_t)(v + 1) * view_stride, qx, qy, qz, h, w, C, w * C, win, w00,
+                           w01, w10, w11);
+            const u64 p00 = pk2(w00, w00), p01 = pk2(w01, w01), p10 = pk2(w10, w10),
+                      p11 = pk2(w11, w11);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              u64 a = mul2(win.t00.v[k], p00);
+              a = fma2(win.t01.v[k], p01, a);
+              a = fma2(win.t10.v[k], p10, a);
+              r[k] = fma2(win.t11.v[k], p11, a);
+            }
+          }
+          if (v == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r1[p][k] = r[k];
+          } else if (d + p < d0 + n) {
+            // S = (ref + r1) + r2, Q = fma(r2, r2, fma(r1, r1, ref^2)); var = Q/V - (S/V)^2
+            u64 o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const u64 S = add2(add2(ref.v[k], r1[p][k]), r[k]);
+              const u64 Q = fma2(r[k], r[k], fma2(r1[p][k], r1[p][k], mul2(ref.v[k], ref.v[k])));
+              const u64 m = mul2(S, inv_v2), mn = mul2(S, ninv_v2);
+              o[k] = fma2(mn, m, mul2(Q, inv_v2));
+            }
+            if (round_tf32) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float lo, hi;
+                unpk2(o[k], lo, hi);
+                o[k] = pk2(round_tf32_f(lo), round_tf32_f(hi));
+              }
+            }
+            if (active) stg256(optr + (size_t)p * hw * C, o);
+          }
+        }
+      }
+      optr += (size_t)PG * hw * C;
+    }
+    optr -= (size_t)(((n + PG - 1) / PG) * PG - n) * hw * C;      // a short last group advanced too far
+    d0 += n;
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 struct MapEntry { const void* p; int BV, h, w, C, BW, BH; CUtensorMap map; };
 static MapEntry g_maps[32];
@@ -575,10 +817,10 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int NSRC, int C, int TW, int TH, bool REUSE, int MINB, bool GWC = false>
+template <int NSRC, int C, int TW, int TH, bool REUSE, int MINB, bool GWC = false, int CP = 8>
 static int launch(const float* feats, const float* proj, const Hyp& dv, float* cost, int B, int D,
                   int h, int w, int rnd, cudaStream_t st) {
-  constexpr int NT = TW * TH * (C / kCPT);
+  constexpr int NT = TW * TH * (C / CP);
   // box = tile + margins: sweep of the depth run + scale/rotation of the view + the 2x2 window
   static const int mx = env_int("CASMVS_K1_MARGIN_X", NSRC <= 2 ? 16 : 8);
   static const int my = env_int("CASMVS_K1_MARGIN_Y", NSRC <= 2 ? 4 : 3);
@@ -586,7 +828,7 @@ static int launch(const float* feats, const float* proj, const Hyp& dv, float* c
   const int BW = TW + mx, BH = TH + my;
   const int box_stride = (BW * BH * C * 4 + 1023) & ~1023;
   const size_t smem = (size_t)NSRC * box_stride + sizeof(Small) + 1024;
-  auto kfn = warp_var_smem_kernel<NSRC, C, TW, TH, REUSE, MINB, GWC>;
+  auto kfn = warp_var_smem_kernel<NSRC, C, TW, TH, REUSE, MINB, GWC, CP>;
   static std::atomic<bool> attr_set[kMaxDevices];
   if (int rc = opt_in_smem(kfn, 200 * 1024, attr_set, "warp_cost")) return rc;
   if (smem > 200 * 1024) return 1;
@@ -632,6 +874,33 @@ static int launch_dedup(const float* feats, const float* proj, const Hyp& dv, fl
   return after_launch("warp_cost(smem,dedup)");
 }
 
+template <int C, int TW, int TH, int PG, int MINB>
+static int launch_pg(const float* feats, const float* proj, const Hyp& dv, float* cost, int B, int D,
+                     int h, int w, int rnd, cudaStream_t st) {
+  constexpr int NSRC = 2, NT = TW * TH * (C / kCPT);
+  static const int mx = env_int("CASMVS_K1_MARGIN_X", 16);
+  static const int my = env_int("CASMVS_K1_MARGIN_Y", 4);
+  static const int dc_env = env_int("CASMVS_K1S_DCHUNK", 0);
+  const int BW = TW + mx, BH = TH + my;
+  const int box_stride = (BW * BH * C * 4 + 1023) & ~1023;
+  const size_t smem = (size_t)NSRC * box_stride + sizeof(Small) + 1024;
+  auto kfn = warp_var_smem_pg_kernel<C, TW, TH, PG, MINB>;
+  static std::atomic<bool> attr_set[kMaxDevices];
+  if (int rc = opt_in_smem(kfn, 200 * 1024, attr_set, "warp_cost")) return rc;
+  if (smem > 200 * 1024) return 1;
+  CUtensorMap map;
+  if (!feature_map(&map, feats, B * (NSRC + 1), h, w, C, BW, BH)) return -2;
+  const int tiles_x = (w + TW - 1) / TW, tiles_y = (h + TH - 1) / TH;
+  int dchunk = dc_env > 0 ? dc_env : (D <= 16 ? D : 16);
+  while (dc_env <= 0 && dchunk > 4 &&
+         (long)tiles_x * tiles_y * B * ((D + dchunk - 1) / dchunk) < (long)num_sms() * 8)
+    dchunk = (dchunk + 1) / 2;
+  dim3 grd((unsigned)(tiles_x * tiles_y), (unsigned)B, (unsigned)((D + dchunk - 1) / dchunk));
+  kfn<<<grd, NT, smem, st>>>(map, feats, proj, dv, cost, D, h, w, dchunk, BW, BH, box_stride,
+                             tiles_x, rnd);
+  return after_launch("warp_cost(smem,pg)");
+}
+
 }  // namespace k1s
 
 // Variance cost volume, channels-last features and output.  Returns 0 when handled, 1 when the
@@ -670,6 +939,26 @@ int warp_var_smem(const float* feats, const float* proj, const Hyp& dv, float* c
   K1D(7, 16, 32, 2, true, 3) K1D(7, 32, 16, 2, true, 3) K1S(7, 2, 8, 32, 4, true, 3)
   K1D(8, 16, 32, 2, false, 5) K1D(8, 32, 16, 2, false, 5) K1S(8, 2, 8, 32, 4, false, 5)
 #undef K1D
+  // 10..: plane groups (window reuse inside a short walk over PG planes of one view)
+#define K1P(VAR, CC, TW_, TH_, PG_, MB) \
+  if (variant == VAR && V - 1 == 2 && C == CC) return launch_pg<CC, TW_, TH_, PG_, MB>(feats, proj, dv, cost, B, D, h, w, rnd, st);
+  K1P(10, 8, 32, 4, 2, 5) K1P(10, 16, 32, 2, 2, 5) K1P(10, 32, 16, 2, 2, 5)
+  K1P(11, 8, 32, 4, 4, 4) K1P(11, 16, 32, 2, 4, 4) K1P(11, 32, 16, 2, 4, 4)
+  K1P(12, 8, 32, 4, 4, 5) K1P(12, 16, 32, 2, 4, 5) K1P(12, 32, 16, 2, 4, 5)
+  K1P(13, 8, 32, 4, 8, 4) K1P(13, 16, 32, 2, 8, 4) K1P(13, 32, 16, 2, 8, 4)
+  K1P(14, 8, 32, 4, 4, 3) K1P(14, 16, 32, 4, 4, 2) K1P(14, 32, 16, 4, 4, 2)
+  K1P(15, 8, 32, 4, 8, 3) K1P(15, 16, 32, 2, 8, 3) K1P(15, 32, 16, 2, 8, 3)
+  K1P(16, 8, 32, 4, 2, 4) K1P(16, 16, 32, 2, 2, 4) K1P(16, 32, 16, 2, 2, 4)
+  K1P(17, 8, 32, 2, 4, 8) K1P(17, 16, 16, 2, 4, 8) K1P(17, 32, 8, 2, 4, 8)
+#undef K1P
+  // 20..: 16 channels per thread at C = 16 / 32 (C = 8 as variant 4)
+#define K1W(VAR, CC, TW_, TH_, MB) \
+  if (variant == VAR && V - 1 == 2 && C == CC) return launch<2, CC, TW_, TH_, false, MB, false, 16>(feats, proj, dv, cost, B, D, h, w, rnd, st);
+  K1W(20, 16, 32, 4, 3) K1W(20, 32, 16, 4, 3) K1S(20, 2, 8, 32, 4, false, 5)
+  K1W(21, 16, 32, 4, 4) K1W(21, 32, 16, 4, 4) K1S(21, 2, 8, 32, 4, false, 5)
+  K1W(22, 16, 32, 2, 6) K1W(22, 32, 16, 2, 6) K1S(22, 2, 8, 32, 4, false, 5)
+  K1W(23, 16, 32, 2, 8) K1W(23, 32, 16, 2, 8) K1S(23, 2, 8, 32, 4, false, 5)
+#undef K1W
   if (V - 1 == 2) return 1;
   K1S(variant, 1, 8, 32, 4, true, 4) K1S(variant, 1, 16, 32, 4, true, 2) K1S(variant, 1, 32, 16, 4, true, 2)
   K1S(variant, 4, 8, 32, 4, false, 4) K1S(variant, 4, 16, 32, 4, false, 2) K1S(variant, 4, 32, 16, 4, false, 2)

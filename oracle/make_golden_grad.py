@@ -29,12 +29,22 @@ GRAD_KEYS = ["feature.conv0.0.conv.weight", "feature.conv2.2.bn.weight", "featur
              "cost_reg_0.prob.weight", "cost_reg_0.prob.bias"]
 
 
+def training_state_dict(G):
+    """seeded_state_dict with the x50 scaling of prob.weight undone: that scaling makes the softmax
+    nearly one-hot (a sharp parity target for INFERENCE), which makes the GRADIENTS exponentially
+    sensitive to the forward rounding (a 2.7e-3 forward difference moved them by 20-80 %)."""
+    sd = seeded_state_dict((8, 32, 48), (1, 2, 4), G, seed=0)
+    for l in range(3):
+        sd[f"cost_reg_{l}.prob.weight"] = sd[f"cost_reg_{l}.prob.weight"] / 50.0
+    return sd
+
+
 def case(tag, G, W, H, V, seed):
     mvsnet, modules, abn = ref_loader.load_reference_models()
     spec = importlib.util.spec_from_file_location("ref_losses", os.path.join(ref_loader.REFERENCE_ROOT, "losses.py"))
     losses = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(losses)
-    sd = seeded_state_dict((8, 32, 48), (1, 2, 4), G, seed=0)
+    sd = training_state_dict(G)
     model = mvsnet.CascadeMVSNet(num_groups=G, norm_act=abn)
     model.load_state_dict(sd)
     model.train()

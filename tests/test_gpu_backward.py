@@ -12,7 +12,7 @@ from casmvsnet_pl_b200 import ABN, autograd as AG, ops, synth      # noqa: E402
 from casmvsnet_pl_b200.models.mvsnet import CascadeMVSNet          # noqa: E402
 from oracle import casmvs_oracle as O                              # noqa: E402
 from oracle.make_golden import sd_checksum, seeded_state_dict      # noqa: E402
-from oracle.make_golden_grad import GRAD_KEYS                      # noqa: E402
+from oracle.make_golden_grad import GRAD_KEYS, training_state_dict  # noqa: E402
 
 DEV = "cuda:0"
 
@@ -103,7 +103,7 @@ def sl1_loss(res, targets, masks):
 def test_training_step_vs_reference_golden(golden, tag):
     g = golden("train_step_" + tag)
     G, W, H, V, seed = (int(g[k]) for k in ("G", "W", "H", "V", "seed"))
-    sd = seeded_state_dict((8, 32, 48), (1, 2, 4), G, seed=0)
+    sd = training_state_dict(G)
     if sd_checksum(sd) != float(g["sd_checksum"]):
         pytest.skip("torch RNG/init drifted from the fixture's build; regenerate goldens")
     model = CascadeMVSNet(num_groups=G, norm_act=ABN)
@@ -124,6 +124,12 @@ def test_training_step_vs_reference_golden(golden, tag):
     params = dict(model.named_parameters())
     worst = 0.0
     for k in GRAD_KEYS:
+        if k.endswith("prob.bias"):
+            # softmax is shift-invariant: the bias gradient is exactly zero in exact arithmetic,
+            # what both implementations hold is rounding noise
+            scale = g["grad/" + k.replace("bias", "weight")].abs().max().item()
+            assert params[k].grad.abs().max().item() < 1e-3 * scale
+            continue
         r = rel(params[k].grad.cpu(), g["grad/" + k])
         worst = max(worst, r)
         print(f"  grad {k}: rel-L2 {r:.3e}")

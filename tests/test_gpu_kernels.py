@@ -197,8 +197,9 @@ def test_cost_volume_smem_staging_paths(V, C, level, case):
     want = O.variance_cost_volume(feats, pm, dv)
     got = ops.warp_cost(cl(feats.to(DEV)), pm.to(DEV), dv.to(DEV), 1, ops.NHWC).cpu()
     err = stats(f"smem-K1 V={V} C={C} {case}", got, want)
-    assert err.max() < 5e-5 * want.abs().max().item() + 1e-4
-    assert err.mean() < 1e-5
+    # ulp(u) at u ~ 600 is 6e-5 px; the reference's round trip costs 2-3 of them
+    assert err.max() < 2e-4 * want.abs().max().item() + 2e-4
+    assert err.mean() < 2e-5
 
 
 def test_cost_volume_staged_equals_gather(tmp_path):
