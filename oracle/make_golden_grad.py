@@ -67,6 +67,23 @@ def case(tag, G, W, H, V, seed):
         out[f"mask_{l}"] = masks[f"level_{l}"]
     for k in GRAD_KEYS:
         out["grad/" + k] = params[k].grad
+    # the same step in float64: what exact arithmetic gives, to judge which fp32 digits mean anything
+    model64 = mvsnet.CascadeMVSNet(num_groups=G, norm_act=abn)
+    model64.load_state_dict(sd)
+    model64 = model64.double().train()
+    # the reference builds its pixel grid in float32 (kornia create_meshgrid): for the float64
+    # run only, hand it the same grid in float64 (integers: exact in both)
+    orig_grid = modules.create_meshgrid
+    modules.create_meshgrid = lambda *a, **k: orig_grid(*a, **k).double()
+    try:
+        res64 = model64(imgs.double(), pm.double(), dmin, dint)
+    finally:
+        modules.create_meshgrid = orig_grid
+    loss64 = losses.SL1Loss()(res64, {k: v.double() for k, v in targets.items()}, masks)
+    loss64.backward()
+    p64 = dict(model64.named_parameters())
+    for k in GRAD_KEYS:
+        out["grad64/" + k] = p64[k].grad.float()
     path = os.path.join(ROOT, "tests", "golden", f"train_step_{tag}.npz")
     np.savez_compressed(path, **{k: (v.numpy() if torch.is_tensor(v) else np.asarray(v))
                                  for k, v in out.items()})

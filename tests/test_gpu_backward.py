@@ -91,6 +91,46 @@ def test_regress_backward_vs_torch(D):
     assert rel(lg.grad.cpu(), logits.grad) < 1e-5
 
 
+@pytest.mark.parametrize("cin,D,h,w", [(16, 32, 32, 48), (8, 8, 64, 96), (32, 48, 16, 24)])
+def test_costreg_backward_vs_oracle(cin, D, h, w):
+    """The whole 3D U-Net (eval-mode norm-act, parameters trainable) at the volume shapes of the
+    96x64 training goldens -- depth 1 at 1/8 resolution included -- against torch autograd of the
+    oracle's CostRegNet on the CPU: gradients of every parameter and of the input."""
+    from casmvsnet_pl_b200.models.mvsnet import CostRegNet
+    torch.manual_seed(cin)
+    net = CostRegNet(cin, ABN)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for m in net.modules():
+            if hasattr(m, "running_var"):
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+                m.running_mean.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.bias.shape, generator=g) + 0.5)
+    net.eval()
+    x = torch.randn(1, cin, D, h, w, generator=g)
+    up = torch.randn(1, 1, D, h, w, generator=g)
+    sd = {"r." + k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and k.split(".")[-1] in ("weight", "bias"))
+          for k, v in net.state_dict().items()}
+    xc = x.clone().requires_grad_(True)
+    want = O.cost_regularize(xc, sd, "r.")
+    (want * up).sum().backward()
+    net = net.to(DEV)
+    xg = x.to(DEV).requires_grad_(True)
+    got = net(xg)
+    (got * up.to(DEV)).sum().backward()
+    assert rel(got.detach().cpu(), want.detach()) < 1e-5
+    assert rel(xg.grad.cpu(), xc.grad) < 1e-4
+    worst = 0.0
+    for k, p in net.named_parameters():
+        r = rel(p.grad.cpu(), sd["r." + k].grad)
+        worst = max(worst, r)
+        if r > 1e-4:
+            print(f"  {k}: rel-L2 {r:.3e}")
+    print(f"CostRegNet({cin}) {D}x{h}x{w}: worst parameter-gradient rel-L2 {worst:.2e}")
+    assert worst < 2e-4
+
+
 def sl1_loss(res, targets, masks):
     """reference losses.py:10-17"""
     loss = 0
@@ -130,10 +170,16 @@ def test_training_step_vs_reference_golden(golden, tag):
             scale = g["grad/" + k.replace("bias", "weight")].abs().max().item()
             assert params[k].grad.abs().max().item() < 1e-3 * scale
             continue
+        # three numbers per gradient: ours vs the reference's fp32 run, and both against the
+        # reference run in float64.  The loss has random-sign per-pixel gradients, so weight
+        # gradients are heavily cancelling sums: the fp32 reference itself is only good to
+        # 1e-3..1e-2 on some layers.  Requirement: no less accurate than the reference.
         r = rel(params[k].grad.cpu(), g["grad/" + k])
-        worst = max(worst, r)
-        print(f"  grad {k}: rel-L2 {r:.3e}")
-    # fp32 chains of ~40 layers with batch-statistics norms, GPU vs CPU summation orders
-    assert worst < 5e-3
+        e_ours = rel(params[k].grad.cpu(), g["grad64/" + k])
+        e_ref = rel(g["grad/" + k], g["grad64/" + k])
+        worst = max(worst, e_ours / max(e_ref, 2e-5))
+        print(f"  grad {k}: vs ref-fp32 {r:.2e} | vs fp64: ours {e_ours:.2e}, ref-fp32 {e_ref:.2e}")
+        assert e_ours < max(3.0 * e_ref, 1e-4), k
+    print(f"worst (ours vs fp64) / (reference-fp32 vs fp64) = {worst:.2f}")
     # every parameter received a gradient
     assert all(p.grad is not None for p in model.parameters())
