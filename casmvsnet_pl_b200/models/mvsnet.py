@@ -405,6 +405,11 @@ class CascadeMVSNet(nn.Module):
         FeatureNet through its torch modules (host glue), every cascade stage through the
         autograd wrappers of K1 / K2 / K3; hypotheses are detached like mvsnet.py:231."""
         B, V, _, H, W = imgs.shape
+        # The 2D FeatureNet trains through torch / cuDNN.  cuDNN's fp32 convolutions default to
+        # TF32 on this GPU, and the BACKWARD convolutions run later, outside any context manager
+        # around this forward: the flag has to be set process-wide.  The reference is fp32
+        # (opt.py:69-70), so fp32 precision means fp32 here too.
+        torch.backends.cudnn.allow_tf32 = self.precision == "tf32"
         feats = self.feature(imgs.reshape(B * V, 3, H, W))
         proj_by_level = proj_mats.permute(2, 0, 1, 3, 4).contiguous()
         results = {}
