@@ -469,7 +469,7 @@ def main():
             peak, peak_src = measured_peak_hbm()
             flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
             per_stage_bytes = k1_algorithmic_bytes(VIEWS)
-            stage_ms = []
+            stage_ms, stage_ms_mat = [], []
             with torch.no_grad():
                 feats = model.feature(imgs_d.reshape(B * VIEWS, 3, H_IMG, W_IMG))
                 for i, l in enumerate((2, 1, 0)):
@@ -477,29 +477,45 @@ def main():
                     f = f.view(B, VIEWS, *f.shape[1:])
                     D = N_DEPTHS[l]
                     h, w = f.shape[-2:]
-                    dv = ops.uniform_hypotheses(dmin + 3.0 * l, dint * RATIOS[l], D, B, h, w, dev)
                     pml = pm_d[:, :, l].contiguous()
-                    ts = []
-                    for it in range(3 + 10):
-                        flush.zero_()
-                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        e0.record()
-                        ops.warp_cost(f, pml, dv, 1, ops.NHWC)
-                        e1.record()
-                        torch.cuda.synchronize()
-                        if it >= 3:
-                            ts.append(e0.elapsed_time(e1))
-                    stage_ms.append(sum(ts) / len(ts))
+                    # the shipped cascade hands K1 the hypothesis LADDER (first + step*d, generated
+                    # in the kernel); the materialised (B,D,h,w) form of the public API is timed too
+                    lad = ops.Ladder(dmin + 3.0 * l, dint * RATIOS[l], D, B, h, w, dev)
+                    dv = lad.materialize()
+                    use_ladder = model.fuse_hypotheses and ops.ladder_supported(VIEWS, f.shape[2], 1)
+                    forms = [("ladder", lambda: ops.warp_cost_ladder(f, pml, lad, 1))] if use_ladder else []
+                    forms.append(("tensor", lambda: ops.warp_cost(f, pml, dv, 1, ops.NHWC)))
+                    res_ms = {}
+                    for name, fn in forms:
+                        ts = []
+                        for it in range(3 + 10):
+                            flush.zero_()
+                            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            e0.record()
+                            fn()
+                            e1.record()
+                            torch.cuda.synchronize()
+                            if it >= 3:
+                                ts.append(e0.elapsed_time(e1))
+                        res_ms[name] = sum(ts) / len(ts)
+                    stage_ms.append(res_ms.get("ladder", res_ms["tensor"]))
+                    stage_ms_mat.append(res_ms["tensor"])
             tot_bytes = sum(per_stage_bytes)
             tot_ms = sum(stage_ms)
             achieved = tot_bytes / (tot_ms * 1e-3) / 1e9
-            roofline = {"kernel": "warp_cost_kernel (K1, fused warp+variance), 3 launches / depth map",
+            roofline = {"kernel": "warp_var_smem kernel (K1, TMA-staged fused warp+variance), 3 launches / depth map",
                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                         "per_stage": [{"level": l, "algorithmic_bytes": b, "ms": m,
                                        "GBps": b / (m * 1e-3) / 1e9}
                                       for l, b, m in zip((2, 1, 0), per_stage_bytes, stage_ms)],
-                        "l2": "flushed (256 MiB memset) before every timed launch"}
+                        "l2": "flushed (256 MiB memset) before every timed launch",
+                        "hypotheses": ("ladder first + step*d generated in the kernel (what "
+                                       "CascadeMVSNet.forward runs); algorithmic bytes keep the API-level "
+                                       "D*h*w hypothesis term (SURVEY.md 8d)") if stage_ms != stage_ms_mat
+                                      else "materialised (B,D,h,w) tensor",
+                        "materialised_hypotheses": {"ms": stage_ms_mat,
+                                                    "frac": tot_bytes / (sum(stage_ms_mat) * 1e-3) / 1e9 / peak}}
             prof = os.path.join(ROOT, "profiles", "k1_traffic.json")
             if os.path.isfile(prof):
                 try:
@@ -512,13 +528,7 @@ def main():
                 for l in (2, 1, 0):
                     f = feats[f"level_{l}"]
                     f = f.view(B, VIEWS, *f.shape[1:])
-                    D = N_DEPTHS[l]
-                    h, w = f.shape[-2:]
-                    if l == 2:
-                        dv = ops.uniform_hypotheses(dmin, dint * RATIOS[l], D, B, h, w, dev)
-                    else:
-                        dv = ops.depth_hypotheses(depth_l, D, dint * RATIOS[l], upsample=True)
-                    depth_l, _ = model.predict_depth(f, pm_d[:, :, l], dv, getattr(model, f"cost_reg_{l}"))
+                    depth_l, _ = model.run_stage(l, f, pm_d[:, :, l].contiguous(), depth_l, dmin, dint)
             with torch.no_grad():
                 for _ in range(3):
                     hot_only()

@@ -692,13 +692,20 @@ warp_var_smem_pg_kernel(const __grid_constant__ CUtensorMap fmap, const float* _
     int kx[NSRC], ky[NSRC];
 #pragma unroll
     for (int v = 0; v < NSRC; ++v) { kx[v] = kMagicBits + bx[v]; ky[v] = kMagicBits + by[v]; }
+    // hypotheses of the next plane group are fetched while the current one is processed
+    float dnext[PG];
+#pragma unroll
+    for (int p = 0; p < PG; ++p) dnext[p] = hp.at(min(d0 + p, d0 + n - 1));
     mbar_wait(bar, phase);
     phase ^= 1;
 
     for (int d = d0; d < d0 + n; d += PG) {
       float inv_d[PG];
 #pragma unroll
-      for (int p = 0; p < PG; ++p) inv_d[p] = rcp_approx(hp.at(min(d + p, d0 + n - 1)));
+      for (int p = 0; p < PG; ++p) {
+        inv_d[p] = rcp_approx(dnext[p]);
+        dnext[p] = hp.at(min(d + PG + p, d0 + n - 1));
+      }
       u64 r1[PG][4];
 #pragma unroll
       for (int v = 0; v < NSRC; ++v) {
@@ -923,7 +930,7 @@ int warp_var_smem(const float* feats, const float* proj, const Hyp& dv, float* c
   }
   // tile / register-budget variants (CASMVS_K1S_VARIANT; defaults measured on cfg2, see
   // profiles/r2_k1_variants.jsonl): {tile, REUSE windows in registers, min resident CTAs}
-  static const int variant = env_int("CASMVS_K1S_VARIANT", 4);
+  static const int variant = env_int("CASMVS_K1S_VARIANT", 16);
 #define K1S(VAR, NS, CC, TW_, TH_, RU, MB) \
   if (variant == VAR && V - 1 == NS && C == CC) return launch<NS, CC, TW_, TH_, RU, MB>(feats, proj, dv, cost, B, D, h, w, rnd, st);
   K1S(0, 2, 8, 32, 4, true, 4) K1S(0, 2, 16, 32, 4, true, 2) K1S(0, 2, 32, 16, 4, true, 2)

@@ -433,6 +433,32 @@ class CascadeMVSNet(nn.Module):
             results[f"confidence_{l}"] = confidence_l
         return results
 
+    def run_stage(self, l, feats_l, proj_mats_l, depth_prev, init_depth_min, depth_interval):
+        """One cascade stage of the inference path (no grad): hypotheses -> K1 -> K2 -> K3.
+        feats_l (B,V,C,h,w) channels-last, proj_mats_l (B,V-1,3,4), depth_prev (B,h/2,w/2) or None
+        for the coarsest stage.  Returns depth, confidence (B,h,w)."""
+        B, V, C, h, w = feats_l.shape
+        D = self.n_depths[l]
+        depth_interval_l = depth_interval * self.interval_ratios[l]
+        cost_reg = getattr(self, f"cost_reg_{l}")
+        if self.fuse_hypotheses and ops.ladder_supported(V, C, self.G) and \
+                ops.is_channels_last_feats(feats_l):
+            first = init_depth_min if depth_prev is None else ops.depth_first(depth_prev, D, depth_interval_l)
+            lad = ops.Ladder(first, depth_interval_l, D, B, h, w, feats_l.device)
+            cost = ops.warp_cost_ladder(feats_l, proj_mats_l, lad, self.G,
+                                        round_tf32=(cost_reg.precision == "tf32"))
+            logits = cost_reg(cost).squeeze(1)
+            del cost
+            depth, confidence, self._last_index = ops.regress_ladder(logits, lad,
+                                                                     want_index=self.return_index)
+            return depth, confidence
+        if depth_prev is None:
+            depth_values = ops.uniform_hypotheses(init_depth_min, depth_interval_l, D, B, h, w,
+                                                  feats_l.device)
+        else:
+            depth_values = ops.depth_hypotheses(depth_prev, D, depth_interval_l, upsample=True)
+        return self.predict_depth(feats_l, proj_mats_l, depth_values, cost_reg)
+
     def forward(self, imgs, proj_mats, init_depth_min, depth_interval):
         """imgs (B,V,3,H,W); proj_mats (B,V-1,levels,3,4) fine->coarse;
         init_depth_min, depth_interval: float or (B,1) tensors.
@@ -464,29 +490,8 @@ class CascadeMVSNet(nn.Module):
                 feats_l = feats[f"level_{l}"]
                 feats_l = feats_l.view(B, V, *feats_l.shape[1:])
                 proj_mats_l = proj_by_level[l]
-                depth_interval_l = depth_interval * self.interval_ratios[l]
-                D = self.n_depths[l]
-                h, w = feats_l.shape[-2:]
-                cost_reg = getattr(self, f"cost_reg_{l}")
-                if self.fuse_hypotheses and ops.ladder_supported(V, feats_l.shape[2], self.G):
-                    first = init_depth_min if l == self.levels - 1 else \
-                        ops.depth_first(depth_l, D, depth_interval_l)
-                    lad = ops.Ladder(first, depth_interval_l, D, B, h, w, imgs.device)
-                    cost = ops.warp_cost_ladder(feats_l, proj_mats_l, lad, self.G,
-                                                round_tf32=(cost_reg.precision == "tf32"))
-                    logits = cost_reg(cost).squeeze(1)
-                    del cost
-                    depth_l, confidence_l, self._last_index = ops.regress_ladder(
-                        logits, lad, want_index=self.return_index)
-                else:
-                    if l == self.levels - 1:
-                        depth_values = ops.uniform_hypotheses(init_depth_min, depth_interval_l, D,
-                                                              B, h, w, imgs.device)
-                    else:
-                        depth_values = ops.depth_hypotheses(depth_l, D, depth_interval_l,
-                                                            upsample=True)
-                    depth_l, confidence_l = self.predict_depth(
-                        feats_l, proj_mats_l, depth_values, cost_reg)
+                depth_l, confidence_l = self.run_stage(l, feats_l, proj_mats_l, depth_l,
+                                                       init_depth_min, depth_interval)
                 results[f"depth_{l}"] = depth_l
                 results[f"confidence_{l}"] = confidence_l
                 if self.return_index:

@@ -25,6 +25,7 @@ ap.add_argument("--gwc", type=int, default=0)
 ap.add_argument("--W", type=int, default=640)
 ap.add_argument("--H", type=int, default=512)
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--ladder", action="store_true", help="hypotheses as first + step*d generated in the kernel (what the cascade runs)")
 ap.add_argument("--profile", action="store_true", help="one launch per level inside cudaProfilerStart/Stop")
 a = ap.parse_args()
 dev = "cuda:0"
@@ -46,15 +47,22 @@ for l, D in ((2, 48), (1, 32), (0, 8)):
         cur = (650 + 40 * torch.sin(3 * xs) * torch.cos(2 * ys)).reshape(1, 1, h, w).to(dev)
         dv = ops.depth_hypotheses(cur, D, 2.65 * (2 if l == 1 else 1))
     pml = pm[:, :, l].contiguous()
+    if a.ladder:
+        step = 2.65 * (4 if l == 2 else 2 if l == 1 else 1)
+        lad = ops.Ladder(425.0 if l == 2 else dv[:, 0].contiguous(), step, D, 1, h, w, dev)
+        assert torch.equal(lad.materialize(), dv)
+        run = lambda: ops.warp_cost_ladder(f, pml, lad, G)            # noqa: E731
+    else:
+        run = lambda: ops.warp_cost(f, pml, dv, G, ops.NHWC)          # noqa: E731
     nbytes = 4 * (V * C * h * w + (C if G == 1 else G) * D * h * w + D * h * w) + 48 * (V - 1)
     if a.profile:
         for _ in range(2):
-            ops.warp_cost(f, pml, dv, G, ops.NHWC)
+            run()
         torch.cuda.synchronize()
         flush.zero_()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStart()
-        ops.warp_cost(f, pml, dv, G, ops.NHWC)
+        run()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
         continue
@@ -63,7 +71,7 @@ for l, D in ((2, 48), (1, 32), (0, 8)):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        o = ops.warp_cost(f, pml, dv, G, ops.NHWC)
+        o = run()
         e1.record()
         torch.cuda.synchronize()
         if it >= 3:
@@ -77,7 +85,7 @@ for l, D in ((2, 48), (1, 32), (0, 8)):
 if not a.profile:
     print(json.dumps(dict(smem=os.environ.get("CASMVS_K1_SMEM", "1"),
                           variant=os.environ.get("CASMVS_K1S_VARIANT", "0"),
-                          margin=os.environ.get("CASMVS_K1_MARGIN_X", "dflt"),
+                          margin=os.environ.get("CASMVS_K1_MARGIN_X", "dflt"), ladder=a.ladder,
                           dchunk=os.environ.get("CASMVS_K1S_DCHUNK", "auto"), views=V, gwc=a.gwc,
                           total_ms=round(tot_ms, 4), GBps=round(tot_b / tot_ms / 1e6, 1),
                           frac_of_peak=round(tot_b / tot_ms / 1e6 / peak, 3), peak=peak, levels=out)))
