@@ -140,3 +140,14 @@ extern "C" int casmvs_invalidate_weight_cache(void) {
 }
 
 extern "C" uint64_t casmvs_weight_cache_generation(void) { return tc::g_generation.load(); }
+
+extern "C" int casmvs_weight_image_count(const void* w_packed, size_t bytes) {
+  std::lock_guard<std::mutex> lock(tc::g_cache_mu);
+  const char* lo = static_cast<const char*>(w_packed);
+  int n = 0;
+  for (auto& e : tc::g_cache) {
+    const char* k = static_cast<const char*>(e.key);
+    if (k >= lo && k < lo + bytes) ++n;
+  }
+  return n;
+}

@@ -38,12 +38,27 @@ class GraphedCascade:
             self.out = model(self.imgs, self.proj, self.dmin, self.dint)
         # libcasmvs kernels recorded in the graph (each replay launches all of them)
         self.kernels_per_replay = _lib.launch_count() - n0
-        # the graph embeds raw pointers to the library's tensor-core operand images
-        self._weight_generation = _lib.weight_cache_generation()
+        # the graph embeds raw pointers to the library's tensor-core operand images: remember
+        # which packed buffers it depends on and how many images each of them has
+        self._deps = [(b, b.data_ptr(), self._image_count(b)) for b in self._packed_buffers()]
+
+    def _packed_buffers(self):
+        fn = getattr(self.model, "packed_buffers", None)
+        return fn() if fn is not None else []
+
+    @staticmethod
+    def _image_count(b):
+        from . import _lib
+        import ctypes
+        return _lib.load().casmvs_weight_image_count(ctypes.c_void_p(b.data_ptr()),
+                                                     b.numel() * b.element_size())
 
     def _check_weights(self):
         from . import _lib
-        if _lib.weight_cache_generation() != self._weight_generation:
+        now = {id(b) for b in self._packed_buffers()}
+        ok = all(id(b) in now and b.data_ptr() == ptr and self._image_count(b) == n
+                 for b, ptr, n in self._deps)
+        if not ok:
             raise _lib.CasMVSError(
                 "packed weights were re-created after this CUDA graph was captured (load_state_dict, "
                 "a second model, ...): the graph references freed operand images; build a new "

@@ -433,6 +433,18 @@ class CascadeMVSNet(nn.Module):
             results[f"confidence_{l}"] = confidence_l
         return results
 
+    def packed_buffers(self):
+        """The packed-weight tensors whose tensor-core operand images a captured CUDA graph of this
+        model embeds (CostRegNet blobs, FeatureNet packs): GraphedCascade watches them."""
+        bufs = []
+        for l in range(self.levels):
+            b = getattr(self, f"cost_reg_{l}")._blob
+            if b is not None:
+                bufs.append(b)
+        f = self.feature
+        bufs += list(getattr(f, "_pack_cache", {}).values()) + list(getattr(f, "_smooth_pack", ()))
+        return [b for b in bufs if torch.is_tensor(b) and b.is_cuda]
+
     def run_stage(self, l, feats_l, proj_mats_l, depth_prev, init_depth_min, depth_interval):
         """One cascade stage of the inference path (no grad): hypotheses -> K1 -> K2 -> K3.
         feats_l (B,V,C,h,w) channels-last, proj_mats_l (B,V-1,3,4), depth_prev (B,h/2,w/2) or None

@@ -135,6 +135,10 @@ int casmvs_pack_conv3d_weights(const float* w_torch, int kind, int Cin, int Cout
 int casmvs_release_weight_images(const void* w_packed, size_t bytes);
 int casmvs_invalidate_weight_cache(void);
 uint64_t casmvs_weight_cache_generation(void);
+/* number of cached images keyed inside [w_packed, w_packed + bytes): a captured graph records
+ * it per packed buffer it depends on and re-checks it before every replay (a release anywhere
+ * else -- another model, a dead model's recycled address -- does not invalidate the graph). */
+int casmvs_weight_image_count(const void* w_packed, size_t bytes);
 int casmvs_conv3d_fwd(const float* x, const float* w_packed, const float* scale,
                       const float* shift, float slope, const float* skip, float* y,
                       int B, int Cin, int Cout, int D, int h, int w, /* INPUT dims */

@@ -281,9 +281,8 @@ def test_weight_image_lifetime_and_graph_generation():
     g = GraphedCascade(model, imgs, pm, dmin, dint, warmup=1)
     gen = _lib.weight_cache_generation()
     other, _ = build(8, "tf32")                     # packs 3 more CostRegNets + a FeatureNet
-    other(imgs, pm, dmin, dint)
-    assert _lib.weight_cache_generation() == gen    # nothing of `model` was dropped
-    out = g()
+    other(imgs, pm, dmin, dint)                     # (may drop stale images of dead models)
+    out = g()                                       # ... which does not invalidate this graph
     assert all(torch.equal(out[k], want[k]) for k in want)
     # in-place edit of a parameter -> re-pack on the next eager call -> old images released
     with torch.no_grad():
@@ -292,6 +291,12 @@ def test_weight_image_lifetime_and_graph_generation():
     assert _lib.weight_cache_generation() > gen
     with pytest.raises(_lib.CasMVSError):
         g()
+    # the other model's graph is untouched by all of this
+    g2 = GraphedCascade(other, imgs, pm, dmin, dint, warmup=1)
+    want2 = {k: v.clone() for k, v in other(imgs, pm, dmin, dint).items()}
+    del model, g
+    out2 = g2()
+    assert all(torch.equal(out2[k], want2[k]) for k in want2)
 
 
 @pytest.mark.parametrize("G", [1, 8])
