@@ -693,7 +693,7 @@ extern "C" int casmvs_warp_cost_ladder_fwd(const float* feats, const float* proj
   const int rc = warp_var_smem(feats, proj, hyp, cost, B, V, C, D, h, w, num_groups,
                                round_tf32 ? 1 : 0, as_stream(stream));
   if (rc == 1) {
-    set_error("warp_cost_ladder: shape not covered by the staged kernel (V-1 in {1,2,4,6}, C in "
+    set_error("warp_cost_ladder: shape not covered by the staged kernel (V-1 in {1,2}, C in "
               "{8,16,32}, groups 1 or 8, channels-last features): materialise the hypotheses and "
               "call casmvs_warp_cost_fwd (got V=%d C=%d G=%d)", V, C, num_groups);
     return -1;

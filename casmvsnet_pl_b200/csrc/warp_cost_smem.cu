@@ -634,6 +634,12 @@ warp_var_smem_pg_kernel(const __grid_constant__ CUtensorMap fmap, const float* _
   const HypPix hp(hyp, b, D, (size_t)hw, pix);
   float* optr = cost + ((size_t)(b * D + d_begin) * hw + pix) * C + c0;
   const int row_b = BW * TEXB;
+  // a row pitch that is a multiple of 1024 B leaves the swizzle bits of an address unchanged:
+  // the second window row is then the first one + row_b (launch_pg picks BW accordingly)
+  const bool rowal = (row_b & 1023) == 0;
+  u64 refsq[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) refsq[k] = mul2(ref.v[k], ref.v[k]);
   uint32_t phase = 0;
 
   for (int d0 = d_begin; d0 < d_end;) {
@@ -728,10 +734,11 @@ warp_var_smem_pg_kernel(const __grid_constant__ CUtensorMap fmap, const float* _
             const float wxa = 1.f - fx, wya = 1.f - fy;
             const int l00 = v * box_stride + yi * row_b + xi * TEXB + c0 * 4;
             if (l00 != cur) {
-              lds_tex(base + swz<TEXB>(l00), t00);
-              lds_tex(base + swz<TEXB>(l00 + TEXB), t01);
-              lds_tex(base + swz<TEXB>(l00 + row_b), t10);
-              lds_tex(base + swz<TEXB>(l00 + row_b + TEXB), t11);
+              const uint32_t a0 = base + swz<TEXB>(l00), a1 = base + swz<TEXB>(l00 + TEXB);
+              lds_tex(a0, t00);
+              lds_tex(a1, t01);
+              lds_tex(rowal ? a0 + row_b : base + swz<TEXB>(l00 + row_b), t10);
+              lds_tex(rowal ? a1 + row_b : base + swz<TEXB>(l00 + row_b + TEXB), t11);
               cur = l00;
             }
             const float w00 = wxa * wya, w01 = fx * wya, w10 = wxa * fy, w11 = fx * fy;
@@ -768,7 +775,7 @@ warp_var_smem_pg_kernel(const __grid_constant__ CUtensorMap fmap, const float* _
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const u64 S = add2(add2(ref.v[k], r1[p][k]), r[k]);
-              const u64 Q = fma2(r[k], r[k], fma2(r1[p][k], r1[p][k], mul2(ref.v[k], ref.v[k])));
+              const u64 Q = fma2(r[k], r[k], fma2(r1[p][k], r1[p][k], refsq[k]));
               const u64 m = mul2(S, inv_v2), mn = mul2(S, ninv_v2);
               o[k] = fma2(mn, m, mul2(Q, inv_v2));
             }
@@ -888,7 +895,9 @@ static int launch_pg(const float* feats, const float* proj, const Hyp& dv, float
   static const int mx = env_int("CASMVS_K1_MARGIN_X", 16);
   static const int my = env_int("CASMVS_K1_MARGIN_Y", 4);
   static const int dc_env = env_int("CASMVS_K1S_DCHUNK", 0);
-  const int BW = TW + mx, BH = TH + my;
+  // box width rounded up so that the row pitch BW * C * 4 is a multiple of 1024 B (see rowal)
+  const int wq = 1024 / (C * 4);
+  const int BW = (TW + mx + wq - 1) / wq * wq, BH = TH + my;
   const int box_stride = (BW * BH * C * 4 + 1023) & ~1023;
   const size_t smem = (size_t)NSRC * box_stride + sizeof(Small) + 1024;
   auto kfn = warp_var_smem_pg_kernel<C, TW, TH, PG, MINB>;
@@ -918,12 +927,18 @@ int warp_var_smem(const float* feats, const float* proj, const Hyp& dv, float* c
   if (!enabled) return 1;
   if ((reinterpret_cast<uintptr_t>(feats) & 15) != 0 || B > 65535) return 1;
   using namespace k1s;
+  // Measured (profiles/r2_k1_variants.txt): with 4 / 6 source views the staged boxes leave one
+  // CTA per SM and the gather kernels of warp_cost.cu are 1.2x / 1.9x faster (cfg4 / cfg5
+  // shapes), so those shapes are left to them unless CASMVS_K1S_MANYVIEWS=1.
+  static const int many = env_int("CASMVS_K1S_MANYVIEWS", 0);
+  if (V - 1 > 2 && !many) return 1;
   if (num_groups != 1) {
-    // group-wise correlation: the reference's default G = 8, source views as in cfg3
+    // group-wise correlation: the reference's default G = 8
     if (num_groups != 8) return 1;
 #define K1G(NS, CC, TW_, TH_, MB) \
-  if (V - 1 == NS && C == CC) return launch<NS, CC, TW_, TH_, NS <= 2, MB, true>(feats, proj, dv, cost, B, D, h, w, rnd, st);
-    K1G(2, 8, 32, 4, 4) K1G(2, 16, 32, 4, 2) K1G(2, 32, 16, 4, 2)
+  if (V - 1 == NS && C == CC) return launch<NS, CC, TW_, TH_, false, MB, true>(feats, proj, dv, cost, B, D, h, w, rnd, st);
+    K1G(1, 8, 32, 4, 5) K1G(1, 16, 32, 2, 5) K1G(1, 32, 16, 2, 5)
+    K1G(2, 8, 32, 4, 5) K1G(2, 16, 32, 2, 5) K1G(2, 32, 16, 2, 5)
     K1G(4, 8, 32, 4, 4) K1G(4, 16, 32, 4, 2) K1G(4, 32, 16, 4, 2)
 #undef K1G
     return 1;
@@ -967,7 +982,7 @@ int warp_var_smem(const float* feats, const float* proj, const Hyp& dv, float* c
   K1W(23, 16, 32, 2, 8) K1W(23, 32, 16, 2, 8) K1S(23, 2, 8, 32, 4, false, 5)
 #undef K1W
   if (V - 1 == 2) return 1;
-  K1S(variant, 1, 8, 32, 4, true, 4) K1S(variant, 1, 16, 32, 4, true, 2) K1S(variant, 1, 32, 16, 4, true, 2)
+  K1S(variant, 1, 8, 32, 4, false, 5) K1S(variant, 1, 16, 32, 2, false, 5) K1S(variant, 1, 32, 16, 2, false, 5)
   K1S(variant, 4, 8, 32, 4, false, 4) K1S(variant, 4, 16, 32, 4, false, 2) K1S(variant, 4, 32, 16, 4, false, 2)
   K1S(variant, 6, 8, 32, 4, false, 4) K1S(variant, 6, 16, 32, 4, false, 2) K1S(variant, 6, 32, 16, 4, false, 2)
 #undef K1S

@@ -7,8 +7,10 @@
 //   * casmvs_release_weight_images(ptr, bytes) drops every image whose key lies inside
 //     [ptr, ptr + bytes) -- the Python binding calls it whenever it (re)creates a packed buffer,
 //     so an address that the allocator hands out again can never hit a stale image;
-//   * every release bumps casmvs_weight_cache_generation(); a captured CUDA graph holds raw
-//     image pointers, so GraphedCascade compares the generation before each replay.
+//   * a captured CUDA graph holds raw image pointers: GraphedCascade records, per packed buffer
+//     of its model, casmvs_weight_image_count() and re-checks it before each replay (releases
+//     that concern other buffers do not invalidate it; casmvs_weight_cache_generation() counts
+//     all releases).
 // Thread-safe (one mutex); entries carry the stream + event of their builder kernel so that a
 // hit from another stream waits for the build, and programmatic dependent launch (whose
 // prologue reads the image BEFORE griddepcontrol.wait) is only allowed once the build is known

@@ -198,7 +198,7 @@ int casmvs_uniform_hypotheses_fwd(float depth_min, float step, const float* dept
  * scalar `first`; step: `step_b` (B) else the scalar `step`.
  * casmvs_depth_first_fwd writes only the first rung (B,h,w) of casmvs_depth_hypotheses_fwd.
  * casmvs_warp_cost_ladder_fwd: channels-last features and cost volume; shapes of the staged
- * kernel only (V-1 in {1,2,4,6}, C in {8,16,32}, num_groups 1 or 8), error otherwise. */
+ * kernel only (V-1 in {1,2}, C in {8,16,32}, num_groups 1 or 8), error otherwise. */
 int casmvs_depth_first_fwd(const float* cur, int upsample, float half_range, float step,
                            const float* step_dev, float* out, int B, int D, int h, int w,
                            void* stream);
