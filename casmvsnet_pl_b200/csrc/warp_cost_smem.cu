@@ -87,9 +87,9 @@ __device__ __forceinline__ TexP<CP> ldg_texp(const float* p) {
   return t;
 }
 
-// NSRC source views, C channels (8 per thread), TW x TH pixel tile; REUSE: keep the 2x2 windows
-// in registers across planes (64 registers at NSRC = 2).
-template <int NSRC, int C, int TW, int TH, bool REUSE, int MINB, bool GWC = false, int CP = 8>
+// NSRC source views, C channels, TW x TH pixel tile.  Every plane loads its 2x2 windows (the
+// plane-group kernel below re-uses them); variance or 8-group correlation epilogue.
+template <int NSRC, int C, int TW, int TH, int MINB, bool GWC = false, int CP = 8>
 __global__ void __launch_bounds__(TW* TH*(C / CP), MINB)
 warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __restrict__ feats,
                      const float* __restrict__ proj, const Hyp hyp,
@@ -145,8 +145,6 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
   float* optr = cost + ((size_t)(b * D + d_begin) * hw + pix) * COUT + (GWC ? sub * NG : c0);
   const int row_b = BW * TEXB;
 
-  TexP<CP> t00[NSRC], t01[NSRC], t10[NSRC], t11[NSRC];
-  int cl[NSRC];
   uint32_t phase = 0;
 
   for (int d0 = d_begin; d0 < d_end;) {
@@ -210,7 +208,6 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
 #pragma unroll
     for (int v = 0; v < NSRC; ++v) {
       kx[v] = kMagicBits + bx[v]; ky[v] = kMagicBits + by[v];
-      cl[v] = -1;
     }
     float depth_next = hp.at(d0);
     mbar_wait(bar, phase);
@@ -243,23 +240,21 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
           const float fx = u - (fu - kMagic), fy = vv - (fv - kMagic);
           const float wxa = 1.f - fx, wya = 1.f - fy;
           const int l00 = v * box_stride + yi * row_b + xi * TEXB + c0 * 4;
-          if (!REUSE || l00 != cl[v]) {
-            lds_texp<CP>(base + swz<TEXB>(l00), t00[v]);
-            lds_texp<CP>(base + swz<TEXB>(l00 + TEXB), t01[v]);
-            lds_texp<CP>(base + swz<TEXB>(l00 + row_b), t10[v]);
-            lds_texp<CP>(base + swz<TEXB>(l00 + row_b + TEXB), t11[v]);
-            cl[v] = l00;
-          }
+          TexP<CP> t00, t01, t10, t11;
+          lds_texp<CP>(base + swz<TEXB>(l00), t00);
+          lds_texp<CP>(base + swz<TEXB>(l00 + TEXB), t01);
+          lds_texp<CP>(base + swz<TEXB>(l00 + row_b), t10);
+          lds_texp<CP>(base + swz<TEXB>(l00 + row_b + TEXB), t11);
           const float w00 = wxa * wya, w01 = fx * wya, w10 = wxa * fy, w11 = fx * fy;
           const u64 p00 = pk2(w00, w00), p01 = pk2(w01, w01), p10 = pk2(w10, w10),
                     p11 = pk2(w11, w11);
 #pragma unroll
           for (int k = 0; k < NP; ++k) {
             // tap order nw, ne, sw, se like ATen grid_sampler_2d
-            u64 a = mul2(t00[v].v[k], p00);
-            a = fma2(t01[v].v[k], p01, a);
-            a = fma2(t10[v].v[k], p10, a);
-            r[k] = fma2(t11[v].v[k], p11, a);
+            u64 a = mul2(t00.v[k], p00);
+            a = fma2(t01.v[k], p01, a);
+            a = fma2(t10.v[k], p10, a);
+            r[k] = fma2(t11.v[k], p11, a);
           }
         } else if (qz <= 1e-7f || u <= -1.f || u >= (float)w || vv <= -1.f || vv >= (float)h) {
           // behind the camera (modules.py:76-79) or entirely outside the source image: the
@@ -338,238 +333,6 @@ warp_var_smem_kernel(const __grid_constant__ CUtensorMap fmap, const float* __re
         }
       }
       optr += (size_t)hw * C;
-    }
-    d0 += n;
-  }
-}
-
-// ---- variant with the coordinate math shared between the threads of a pixel --------------------
-// At C = 16 / 32 a pixel is served by TPP = 2 / 4 threads (8 channels each) that would all
-// evaluate the same homography, reciprocal, floor and window address for every (plane, view):
-// ~26 fma/alu-pipe instructions each, on the pipe that co-limits this kernel.  Here (2 source
-// views) every thread evaluates ONE (plane, view) pair per step -- TPP = 2: its own view of the
-// current plane; TPP = 4: view (sub & 1) of plane d + (sub >> 1), two planes per step -- and the
-// {window offset, fx, fy} triples travel through warp shuffles (the threads of a pixel are
-// neighbouring lanes).  Variance cost, NSRC = 2; everything else is the kernel above.
-struct Coord { int lbase; float fx, fy; };   // lbase >= 0: window offset in the staged boxes
-                                             // -1: sample is exactly zero, -2: robust gather path
-template <int C, int TW, int TH, bool REUSE, int MINB>
-__global__ void __launch_bounds__(TW* TH*(C / kCPT), MINB)
-warp_var_smem_dedup_kernel(const __grid_constant__ CUtensorMap fmap, const float* __restrict__ feats,
-                           const float* __restrict__ proj, const Hyp hyp,
-                           float* __restrict__ cost, int D, int h, int w, int dchunk, int BW, int BH,
-                           int box_stride, int tiles_x, int round_tf32) {
-  constexpr int NSRC = 2, V = 3, TPP = C / kCPT, TEXB = C * 4, NT = TW * TH * TPP;
-  static_assert(TPP == 2 || TPP == 4, "dedup variant: C = 16 or 32");
-  constexpr int PPS = TPP / 2;                 // planes per step
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  Small* sm = reinterpret_cast<Small*>(smem_raw + (base - smem_u32(smem_raw)) + NSRC * box_stride);
-  const uint32_t bar = smem_u32(&sm->bar);
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int b = blockIdx.y;
-  const int tile_y = blockIdx.x / tiles_x, tile_x = blockIdx.x - tile_y * tiles_x;
-  const int lp = tid / TPP, sub = tid - lp * TPP;
-  const int py = lp / TW, px = lp - py * TW;
-  const int xr = tile_x * TW + px, yr = tile_y * TH + py;
-  const bool active = xr < w && yr < h;
-  const int x = min(xr, w - 1), y = min(yr, h - 1);
-  const int c0 = sub * kCPT;
-  const int hw = h * w, pix = y * w + x;
-  const int mv = sub & 1, mpo = sub >> 1;      // this thread's view and plane offset within a step
-  const int lane0 = lane & ~(TPP - 1);         // first lane of this pixel
-
-  for (int i = tid; i < NSRC * 12; i += NT) sm->proj[i] = proj[(size_t)b * NSRC * 12 + i];
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    fence_barrier_init();
-  }
-  __syncthreads();
-  const float xf = (float)x, yf = (float)y;
-  const float* Pm = sm->proj + mv * 12;
-  const float max_ = fmaf(Pm[0], xf, fmaf(Pm[1], yf, Pm[2]));
-  const float may_ = fmaf(Pm[4], xf, fmaf(Pm[5], yf, Pm[6]));
-  const float maz_ = fmaf(Pm[8], xf, fmaf(Pm[9], yf, Pm[10]));
-  const float mtx = Pm[3], mty = Pm[7], mtz = Pm[11];
-  const size_t view_stride = (size_t)hw * C;
-  const float* fb = feats + (size_t)b * V * view_stride + c0;
-  const Tex8 ref = ldg256(fb + (size_t)pix * C);
-  const float inv_v = 1.f / (float)V;
-  const u64 inv_v2 = pk2(inv_v, inv_v), ninv_v2 = pk2(-inv_v, -inv_v);
-  const int d_begin = blockIdx.z * dchunk;
-  const int d_end = min(D, d_begin + dchunk);
-  const HypPix hp(hyp, b, D, (size_t)hw, pix);
-  float* optr = cost + ((size_t)(b * D + d_begin) * hw + pix) * C + c0;
-  const int row_b = BW * TEXB;
-  Tex8 t00[NSRC], t01[NSRC], t10[NSRC], t11[NSRC];
-  int cl[NSRC];
-  uint32_t phase = 0;
-
-  for (int d0 = d_begin; d0 < d_end;) {
-    int n = d_end - d0;
-    int bx[NSRC], by[NSRC];
-    for (;;) {
-      __syncthreads();
-      if (tid < NSRC * 4) sm->mm[tid] = (tid & 2) ? INT_MIN : INT_MAX;
-      __syncthreads();
-      // footprint: each thread handles its own view (both views are covered by sub 0 / 1)
-      {
-        const float ia = rcp_approx(hp.at(d0));
-        const float ib = rcp_approx(hp.at(d0 + n - 1));
-        int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float id = e ? ib : ia;
-          const float qz = fmaf(mtz, id, maz_);
-          const float rz = rcp_approx(qz);
-          const float u = fmaf(mtx, id, max_) * rz, vv = fmaf(mty, id, may_) * rz;
-          if (active && sub < 2 && qz > 1e-7f && u > -2.f && u < (float)(w + 1) && vv > -2.f &&
-              vv < (float)(h + 1)) {
-            const int xi = __float2int_rd(u), yi = __float2int_rd(vv);
-            mnx = min(mnx, xi); mxx = max(mxx, xi);
-            mny = min(mny, yi); mxy = max(mxy, yi);
-          }
-        }
-        // lanes alternate between the two views: reduce each parity class separately
-#pragma unroll
-        for (int v = 0; v < NSRC; ++v) {
-          const bool me = mv == v;
-          const int a0 = __reduce_min_sync(0xffffffffu, me ? mnx : INT_MAX);
-          const int a1 = __reduce_min_sync(0xffffffffu, me ? mny : INT_MAX);
-          const int a2 = __reduce_max_sync(0xffffffffu, me ? mxx : INT_MIN);
-          const int a3 = __reduce_max_sync(0xffffffffu, me ? mxy : INT_MIN);
-          if (lane == 0) {
-            atomicMin(&sm->mm[v * 4 + 0], a0); atomicMin(&sm->mm[v * 4 + 1], a1);
-            atomicMax(&sm->mm[v * 4 + 2], a2); atomicMax(&sm->mm[v * 4 + 3], a3);
-          }
-        }
-      }
-      __syncthreads();
-      bool fits = true;
-#pragma unroll
-      for (int v = 0; v < NSRC; ++v) {
-        const int mnx = sm->mm[v * 4 + 0], mny = sm->mm[v * 4 + 1];
-        const int mxx = sm->mm[v * 4 + 2], mxy = sm->mm[v * 4 + 3];
-        if (mnx > mxx) { bx[v] = 0; by[v] = 0; continue; }
-        const int sx = mxx + 2 - mnx, sy = mxy + 2 - mny;
-        if (sx > BW || sy > BH) fits = false;
-        bx[v] = mnx - max(0, (BW - sx) >> 1);
-        by[v] = mny - max(0, (BH - sy) >> 1);
-      }
-      if (fits || n == 1) break;
-      n = (n + 1) >> 1;
-    }
-    if (tid == 0) {
-      tma::mbar_expect_tx(bar, (uint32_t)(NSRC * BW * BH * TEXB));
-#pragma unroll
-      for (int v = 0; v < NSRC; ++v)
-        tma::tma_load_4d(base + v * box_stride, &fmap, bar, 0, bx[v], by[v], b * V + v + 1);
-    }
-    const int mkx = kMagicBits + (mv ? bx[1] : bx[0]), mky = kMagicBits + (mv ? by[1] : by[0]);
-    const int mvoff = mv * box_stride;
-    cl[0] = cl[1] = -1;
-    mbar_wait(bar, phase);
-    phase ^= 1;
-
-    for (int d = d0; d < d0 + n; d += PPS) {
-      // this thread's (plane, view): plane d + mpo (clamped: an odd tail computes a dummy)
-      const int dm = min(d + mpo, d0 + n - 1);
-      const float inv_d = rcp_approx(hp.at(dm));
-      Coord mine;
-      {
-        const float qx = fmaf(mtx, inv_d, max_), qy = fmaf(mty, inv_d, may_);
-        const float qz = fmaf(mtz, inv_d, maz_);
-        const float rz = rcp_approx(qz);
-        const float u = qx * rz, vv = qy * rz;
-        const float fu = fadd_rd(u, kMagic), fv = fadd_rd(vv, kMagic);
-        const int xi = __float_as_int(fu) - mkx, yi = __float_as_int(fv) - mky;
-        const bool inbox = (unsigned)xi < (unsigned)(BW - 1) && (unsigned)yi < (unsigned)(BH - 1) &&
-                           qz > 1e-7f;
-        mine.fx = u - (fu - kMagic); mine.fy = vv - (fv - kMagic);
-        mine.lbase = inbox ? mvoff + yi * row_b + xi * TEXB
-                     : (qz <= 1e-7f || u <= -1.f || u >= (float)w || vv <= -1.f || vv >= (float)h) ? -1
-                                                                                               : -2;
-      }
-#pragma unroll
-      for (int pp = 0; pp < PPS; ++pp) {
-        const int dd = d + pp;
-        if (dd >= d0 + n) break;
-        u64 S[4], Q[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { S[k] = ref.v[k]; Q[k] = mul2(ref.v[k], ref.v[k]); }
-#pragma unroll
-        for (int v = 0; v < NSRC; ++v) {
-          const int src = lane0 + 2 * pp + v;                 // the lane that evaluated (dd, v)
-          const int lbase = __shfl_sync(0xffffffffu, mine.lbase, src);
-          const float fx = __shfl_sync(0xffffffffu, mine.fx, src);
-          const float fy = __shfl_sync(0xffffffffu, mine.fy, src);
-          u64 r[4];
-          if (__builtin_expect(lbase >= 0, 1)) {
-            const float wxa = 1.f - fx, wya = 1.f - fy;
-            const int l00 = lbase + c0 * 4;
-            if (!REUSE || l00 != cl[v]) {
-              lds_tex(base + swz<TEXB>(l00), t00[v]);
-              lds_tex(base + swz<TEXB>(l00 + TEXB), t01[v]);
-              lds_tex(base + swz<TEXB>(l00 + row_b), t10[v]);
-              lds_tex(base + swz<TEXB>(l00 + row_b + TEXB), t11[v]);
-              cl[v] = l00;
-            }
-            const float w00 = wxa * wya, w01 = fx * wya, w10 = wxa * fy, w11 = fx * fy;
-            const u64 p00 = pk2(w00, w00), p01 = pk2(w01, w01), p10 = pk2(w10, w10),
-                      p11 = pk2(w11, w11);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              u64 a = mul2(t00[v].v[k], p00);
-              a = fma2(t01[v].v[k], p01, a);
-              a = fma2(t10[v].v[k], p10, a);
-              r[k] = fma2(t11[v].v[k], p11, a);
-            }
-          } else if (lbase == -1) {
-            continue;
-          } else {
-            // robust gather path: re-evaluate the sample from the projection (rare)
-            const float* P = sm->proj + v * 12;
-            const float id = rcp_approx(hp.at(dd));
-            const float qx = fmaf(P[3], id, fmaf(P[0], xf, fmaf(P[1], yf, P[2])));
-            const float qy = fmaf(P[7], id, fmaf(P[4], xf, fmaf(P[5], yf, P[6])));
-            const float qz = fmaf(P[11], id, fmaf(P[8], xf, fmaf(P[9], yf, P[10])));
-            Window win;
-            float w00, w01, w10, w11;
-            sample_view<C>(fb + (size_t)(v + 1) * view_stride, qx, qy, qz, h, w, C, w * C, win, w00,
-                           w01, w10, w11);
-            const u64 p00 = pk2(w00, w00), p01 = pk2(w01, w01), p10 = pk2(w10, w10),
-                      p11 = pk2(w11, w11);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              u64 a = mul2(win.t00.v[k], p00);
-              a = fma2(win.t01.v[k], p01, a);
-              a = fma2(win.t10.v[k], p10, a);
-              r[k] = fma2(win.t11.v[k], p11, a);
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            S[k] = add2(S[k], r[k]);
-            Q[k] = fma2(r[k], r[k], Q[k]);
-          }
-        }
-        u64 o[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const u64 m = mul2(S[k], inv_v2), mn = mul2(S[k], ninv_v2);
-          o[k] = fma2(mn, m, mul2(Q[k], inv_v2));
-        }
-        if (round_tf32) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float lo, hi;
-            unpk2(o[k], lo, hi);
-            o[k] = pk2(round_tf32_f(lo), round_tf32_f(hi));
-          }
-        }
-        if (active) stg256(optr, o);
-        optr += (size_t)hw * C;
-      }
     }
     d0 += n;
   }
@@ -831,7 +594,7 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int NSRC, int C, int TW, int TH, bool REUSE, int MINB, bool GWC = false, int CP = 8>
+template <int NSRC, int C, int TW, int TH, int MINB, bool GWC = false, int CP = 8>
 static int launch(const float* feats, const float* proj, const Hyp& dv, float* cost, int B, int D,
                   int h, int w, int rnd, cudaStream_t st) {
   constexpr int NT = TW * TH * (C / CP);
@@ -842,7 +605,7 @@ static int launch(const float* feats, const float* proj, const Hyp& dv, float* c
   const int BW = TW + mx, BH = TH + my;
   const int box_stride = (BW * BH * C * 4 + 1023) & ~1023;
   const size_t smem = (size_t)NSRC * box_stride + sizeof(Small) + 1024;
-  auto kfn = warp_var_smem_kernel<NSRC, C, TW, TH, REUSE, MINB, GWC, CP>;
+  auto kfn = warp_var_smem_kernel<NSRC, C, TW, TH, MINB, GWC, CP>;
   static std::atomic<bool> attr_set[kMaxDevices];
   if (int rc = opt_in_smem(kfn, 200 * 1024, attr_set, "warp_cost")) return rc;
   if (smem > 200 * 1024) return 1;
@@ -859,33 +622,6 @@ static int launch(const float* feats, const float* proj, const Hyp& dv, float* c
   kfn<<<grd, NT, smem, st>>>(map, feats, proj, dv, cost, D, h, w, dchunk, BW, BH, box_stride,
                              tiles_x, rnd);
   return after_launch("warp_cost(smem)");
-}
-
-template <int C, int TW, int TH, bool REUSE, int MINB>
-static int launch_dedup(const float* feats, const float* proj, const Hyp& dv, float* cost, int B,
-                        int D, int h, int w, int rnd, cudaStream_t st) {
-  constexpr int NSRC = 2, NT = TW * TH * (C / kCPT);
-  static const int mx = env_int("CASMVS_K1_MARGIN_X", 16);
-  static const int my = env_int("CASMVS_K1_MARGIN_Y", 4);
-  static const int dc_env = env_int("CASMVS_K1S_DCHUNK", 0);
-  const int BW = TW + mx, BH = TH + my;
-  const int box_stride = (BW * BH * C * 4 + 1023) & ~1023;
-  const size_t smem = (size_t)NSRC * box_stride + sizeof(Small) + 1024;
-  auto kfn = warp_var_smem_dedup_kernel<C, TW, TH, REUSE, MINB>;
-  static std::atomic<bool> attr_set[kMaxDevices];
-  if (int rc = opt_in_smem(kfn, 200 * 1024, attr_set, "warp_cost")) return rc;
-  if (smem > 200 * 1024) return 1;
-  CUtensorMap map;
-  if (!feature_map(&map, feats, B * (NSRC + 1), h, w, C, BW, BH)) return -2;
-  const int tiles_x = (w + TW - 1) / TW, tiles_y = (h + TH - 1) / TH;
-  int dchunk = dc_env > 0 ? dc_env : (D <= 16 ? D : 16);
-  while (dc_env <= 0 && dchunk > 4 &&
-         (long)tiles_x * tiles_y * B * ((D + dchunk - 1) / dchunk) < (long)num_sms() * 8)
-    dchunk = (dchunk + 1) / 2;
-  dim3 grd((unsigned)(tiles_x * tiles_y), (unsigned)B, (unsigned)((D + dchunk - 1) / dchunk));
-  kfn<<<grd, NT, smem, st>>>(map, feats, proj, dv, cost, D, h, w, dchunk, BW, BH, box_stride,
-                             tiles_x, rnd);
-  return after_launch("warp_cost(smem,dedup)");
 }
 
 template <int C, int TW, int TH, int PG, int MINB>
@@ -936,55 +672,34 @@ int warp_var_smem(const float* feats, const float* proj, const Hyp& dv, float* c
     // group-wise correlation: the reference's default G = 8
     if (num_groups != 8) return 1;
 #define K1G(NS, CC, TW_, TH_, MB) \
-  if (V - 1 == NS && C == CC) return launch<NS, CC, TW_, TH_, false, MB, true>(feats, proj, dv, cost, B, D, h, w, rnd, st);
+  if (V - 1 == NS && C == CC) return launch<NS, CC, TW_, TH_, MB, true>(feats, proj, dv, cost, B, D, h, w, rnd, st);
     K1G(1, 8, 32, 4, 5) K1G(1, 16, 32, 2, 5) K1G(1, 32, 16, 2, 5)
     K1G(2, 8, 32, 4, 5) K1G(2, 16, 32, 2, 5) K1G(2, 32, 16, 2, 5)
     K1G(4, 8, 32, 4, 4) K1G(4, 16, 32, 4, 2) K1G(4, 32, 16, 4, 2)
 #undef K1G
     return 1;
   }
-  // tile / register-budget variants (CASMVS_K1S_VARIANT; defaults measured on cfg2, see
-  // profiles/r2_k1_variants.jsonl): {tile, REUSE windows in registers, min resident CTAs}
+  // Variants (CASMVS_K1S_VARIANT), measured on cfg2 -- profiles/r2_k1_variants.txt:
+  //   16 (default) plane groups of 2: a view's window is re-used across the planes of a group
+  //   11           plane groups of 4
+  //    4           no window reuse (every plane loads its 2x2 windows)
+  // Also measured and removed again: windows of both views kept in registers across ALL planes
+  // (166 registers or spills through the same LSU pipe: 1.2-1.6x slower), coordinate math
+  // shared between the threads of a pixel by warp shuffles (1.2x slower: shuffles use the
+  // bound pipe), 16 channels per thread (1.04x slower: 163 registers, 12 warps per SM).
   static const int variant = env_int("CASMVS_K1S_VARIANT", 16);
-#define K1S(VAR, NS, CC, TW_, TH_, RU, MB) \
-  if (variant == VAR && V - 1 == NS && C == CC) return launch<NS, CC, TW_, TH_, RU, MB>(feats, proj, dv, cost, B, D, h, w, rnd, st);
-  K1S(0, 2, 8, 32, 4, true, 4) K1S(0, 2, 16, 32, 4, true, 2) K1S(0, 2, 32, 16, 4, true, 2)
-  K1S(1, 2, 8, 32, 4, true, 3) K1S(1, 2, 16, 32, 2, true, 3) K1S(1, 2, 32, 16, 2, true, 3)
-  K1S(2, 2, 8, 32, 4, false, 4) K1S(2, 2, 16, 32, 4, false, 2) K1S(2, 2, 32, 16, 4, false, 2)
-  K1S(3, 2, 8, 32, 2, true, 6) K1S(3, 2, 16, 16, 4, true, 3) K1S(3, 2, 32, 8, 4, true, 3)
-  K1S(4, 2, 8, 32, 4, false, 5) K1S(4, 2, 16, 32, 2, false, 5) K1S(4, 2, 32, 16, 2, false, 5)
-  // 5..8: coordinate math shared between the threads of a pixel (C = 16 / 32; C = 8 as variant 0/2)
-#define K1D(VAR, CC, TW_, TH_, RU, MB) \
-  if (variant == VAR && V - 1 == 2 && C == CC) return launch_dedup<CC, TW_, TH_, RU, MB>(feats, proj, dv, cost, B, D, h, w, rnd, st);
-  K1D(5, 16, 32, 4, true, 2) K1D(5, 32, 16, 4, true, 2) K1S(5, 2, 8, 32, 4, true, 4)
-  K1D(6, 16, 32, 4, false, 2) K1D(6, 32, 16, 4, false, 2) K1S(6, 2, 8, 32, 4, false, 4)
-  K1D(7, 16, 32, 2, true, 3) K1D(7, 32, 16, 2, true, 3) K1S(7, 2, 8, 32, 4, true, 3)
-  K1D(8, 16, 32, 2, false, 5) K1D(8, 32, 16, 2, false, 5) K1S(8, 2, 8, 32, 4, false, 5)
-#undef K1D
-  // 10..: plane groups (window reuse inside a short walk over PG planes of one view)
+#define K1S(VAR, NS, CC, TW_, TH_, MB) \
+  if (variant == VAR && V - 1 == NS && C == CC) return launch<NS, CC, TW_, TH_, MB>(feats, proj, dv, cost, B, D, h, w, rnd, st);
 #define K1P(VAR, CC, TW_, TH_, PG_, MB) \
   if (variant == VAR && V - 1 == 2 && C == CC) return launch_pg<CC, TW_, TH_, PG_, MB>(feats, proj, dv, cost, B, D, h, w, rnd, st);
-  K1P(10, 8, 32, 4, 2, 5) K1P(10, 16, 32, 2, 2, 5) K1P(10, 32, 16, 2, 2, 5)
-  K1P(11, 8, 32, 4, 4, 4) K1P(11, 16, 32, 2, 4, 4) K1P(11, 32, 16, 2, 4, 4)
-  K1P(12, 8, 32, 4, 4, 5) K1P(12, 16, 32, 2, 4, 5) K1P(12, 32, 16, 2, 4, 5)
-  K1P(13, 8, 32, 4, 8, 4) K1P(13, 16, 32, 2, 8, 4) K1P(13, 32, 16, 2, 8, 4)
-  K1P(14, 8, 32, 4, 4, 3) K1P(14, 16, 32, 4, 4, 2) K1P(14, 32, 16, 4, 4, 2)
-  K1P(15, 8, 32, 4, 8, 3) K1P(15, 16, 32, 2, 8, 3) K1P(15, 32, 16, 2, 8, 3)
   K1P(16, 8, 32, 4, 2, 4) K1P(16, 16, 32, 2, 2, 4) K1P(16, 32, 16, 2, 2, 4)
-  K1P(17, 8, 32, 2, 4, 8) K1P(17, 16, 16, 2, 4, 8) K1P(17, 32, 8, 2, 4, 8)
+  K1P(11, 8, 32, 4, 4, 4) K1P(11, 16, 32, 2, 4, 4) K1P(11, 32, 16, 2, 4, 4)
+  K1S(4, 2, 8, 32, 4, 5) K1S(4, 2, 16, 32, 2, 5) K1S(4, 2, 32, 16, 2, 5)
 #undef K1P
-  // 20..: 16 channels per thread at C = 16 / 32 (C = 8 as variant 4)
-#define K1W(VAR, CC, TW_, TH_, MB) \
-  if (variant == VAR && V - 1 == 2 && C == CC) return launch<2, CC, TW_, TH_, false, MB, false, 16>(feats, proj, dv, cost, B, D, h, w, rnd, st);
-  K1W(20, 16, 32, 4, 3) K1W(20, 32, 16, 4, 3) K1S(20, 2, 8, 32, 4, false, 5)
-  K1W(21, 16, 32, 4, 4) K1W(21, 32, 16, 4, 4) K1S(21, 2, 8, 32, 4, false, 5)
-  K1W(22, 16, 32, 2, 6) K1W(22, 32, 16, 2, 6) K1S(22, 2, 8, 32, 4, false, 5)
-  K1W(23, 16, 32, 2, 8) K1W(23, 32, 16, 2, 8) K1S(23, 2, 8, 32, 4, false, 5)
-#undef K1W
   if (V - 1 == 2) return 1;
-  K1S(variant, 1, 8, 32, 4, false, 5) K1S(variant, 1, 16, 32, 2, false, 5) K1S(variant, 1, 32, 16, 2, false, 5)
-  K1S(variant, 4, 8, 32, 4, false, 4) K1S(variant, 4, 16, 32, 4, false, 2) K1S(variant, 4, 32, 16, 4, false, 2)
-  K1S(variant, 6, 8, 32, 4, false, 4) K1S(variant, 6, 16, 32, 4, false, 2) K1S(variant, 6, 32, 16, 4, false, 2)
+  K1S(variant, 1, 8, 32, 4, 5) K1S(variant, 1, 16, 32, 2, 5) K1S(variant, 1, 32, 16, 2, 5)
+  K1S(variant, 4, 8, 32, 4, 4) K1S(variant, 4, 16, 32, 4, 2) K1S(variant, 4, 32, 16, 4, 2)
+  K1S(variant, 6, 8, 32, 4, 4) K1S(variant, 6, 16, 32, 4, 2) K1S(variant, 6, 32, 16, 4, 2)
 #undef K1S
   return 1;
 }
