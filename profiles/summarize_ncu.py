@@ -32,7 +32,9 @@ def full(path):
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     want = ["Kernel Name", "launch__grid_size", "launch__registers_per_thread", "gpu__time_duration.sum",
-            "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
+            "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+            "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
             "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
             "lts__throughput.avg.pct_of_peak_sustained_elapsed",
