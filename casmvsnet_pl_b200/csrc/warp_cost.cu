@@ -410,32 +410,16 @@ warp_var_kernel(const float* __restrict__ feats, const float* __restrict__ proj,
   }
 }
 
-int g_k1_cpt = 0;    // CASMVS_K1_CPT  (0 = heuristic, 4 or 8)
-int g_k1_skip = -1;  // CASMVS_K1_SKIP (window reuse across planes; -1 = default)
-
 template <int NSRC, int CT>
 static bool launch_var(cudaStream_t st, const float* f, const float* p, const float* dv,
                        float* cost, int B, int D, int h, int w, int dchunk, int rnd) {
-  const int cpt = g_k1_cpt ? g_k1_cpt : 8;
-  const bool skip = g_k1_skip < 0 ? false : g_k1_skip != 0;   // measured: no gain (kernel is ALU bound)
-  const long threads = (long)h * w * (CT / cpt);
+  // 8 channels per thread, no window skip, 6 resident blocks per SM (80 registers): the best of
+  // the round-1 sweep (profiles/r1_k1_ab_0*.jsonl: 4 channels per thread, window skip and the
+  // 4 / 5 / 8-block register budgets all measured slower and were removed)
+  const long threads = (long)h * w * (CT / 8);
   dim3 grd((unsigned)((threads + kK1Threads - 1) / kK1Threads), (unsigned)B,
            (unsigned)((D + dchunk - 1) / dchunk));
-  // resident blocks per SM the register allocation is asked to allow (CASMVS_K1_MINB, 4..6):
-  // 4 -> 128 registers (all eight taps of both views in flight), 5 -> 96, 6 -> 80, 8 -> 64
-  static int minb = -1;
-  if (minb < 0) {
-    const char* e = getenv("CASMVS_K1_MINB");
-    minb = e ? atoi(e) : 6;     // measured (bench_k1.py): 4 -> 0.186 ms, 5 -> 0.182, 6 -> 0.174
-  }
-#define LV(CPT_, SKIP_, MB_) warp_var_kernel<NSRC, CT, CPT_, SKIP_, MB_><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, D, h, w, dchunk, rnd)
-  if (cpt == 4) { if (skip) LV(4, true, 6); else LV(4, false, 6); }
-  else if (skip) LV(8, true, 4);
-  else if (minb == 5) LV(8, false, 5);
-  else if (minb == 6) LV(8, false, 6);
-  else if (minb == 8) LV(8, false, 8);
-  else LV(8, false, 4);
-#undef LV
+  warp_var_kernel<NSRC, CT, 8, false, 6><<<grd, kK1Threads, 0, st>>>(f, p, dv, cost, D, h, w, dchunk, rnd);
   return true;
 }
 
@@ -603,24 +587,14 @@ extern "C" int casmvs_warp_cost_fwd(const float* feats, int feat_layout, const f
     while (dchunk > 8 && (long)xblocks * B * ((D + dchunk - 1) / dchunk) < want_ctas)
       dchunk = (dchunk + 1) / 2;
   }
-  static bool env2 = false;
-  if (!env2) {
-    env2 = true;
-    if (const char* e = getenv("CASMVS_K1_CPT")) g_k1_cpt = atoi(e);
-    if (const char* e = getenv("CASMVS_K1_SKIP")) g_k1_skip = atoi(e);
-  }
   if (nhwc) {
     // TMA-staged generation (warp_cost_smem.cu): 0 = handled, 1 = shape left to the gather kernels
     const Hyp hyp{depth_values, nullptr, nullptr, nullptr, 0.f, 0.f};
     const int rc = warp_var_smem(f, proj, hyp, cost, B, V, C, D, h, w, num_groups, rnd, st);
     if (rc <= 0) return rc;
   }
-  if (!gwc && nhwc && (V == 3 || V == 2) && (C == 8 || C == 16 || C == 32) &&
-      !(g_k1_cpt != 0 && g_k1_cpt != 4 && g_k1_cpt != 8)) {
-    // hot case (BASELINE cfg2): specialised kernel
-    if (g_k1_cpt == 4 || g_k1_cpt == 0) {
-      // chunking was computed for 8 channels per thread; with 4 there are twice the CTAs
-    }
+  if (!gwc && nhwc && (V == 3 || V == 2) && (C == 8 || C == 16 || C == 32)) {
+    // specialised variance kernel (the round-1 hot case; now behind the staged kernels)
     bool ok = false;
     if (V == 3) {
       if (C == 8) ok = launch_var<2, 8>(st, f, proj, depth_values, cost, B, D, h, w, dchunk, rnd);
