@@ -6,9 +6,9 @@
 //   ConvTranspose3d + norm_act         models/mvsnet.py:74-87
 //   skip additions, prob head          models/mvsnet.py:91-104
 //
-// This is the bit-faithful-products path (CASMVS_FP32) and the path the light
-// strided / transposed layers take; the stride-1 layers that carry ~85 % of
-// the FLOPs run on tcgen05 (conv3d_tc.cu) when TF32 is selected.
+// This is the bit-faithful-products path (CASMVS_FP32: every layer of both networks, the
+// data gradients of the training path) and the counted fallback of the TF32 mode for a layer
+// shape no tcgen05 kernel covers (casmvs_fallback_count; none in the reference architecture).
 //
 // Thread = TW consecutive-w output voxels x COT output channels.  The block's
 // slice of the packed weights ([27][Cin][COT]) sits in shared memory and is read

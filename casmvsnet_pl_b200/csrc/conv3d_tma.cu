@@ -6,12 +6,13 @@
 // (models/modules.py:21-31) and the `prob` head (models/mvsnet.py:89,103) for the
 // stride-1 layers of CostRegNet (conv0, conv2, conv4, conv6, prob).
 //
-// Same GEMM as conv3d_tc.cu (M = 128 voxels = 8(w) x 16(h) of one depth slice, K = Cin per
-// tap, N = 3 x GW: the three kd taps share one A operand), but the input brick of a depth
-// slice (18 x 10 voxels with halo, up to 32 channels) is brought in by ONE TMA tiled load
-// (cp.async.bulk.tensor.5d over x viewed as {C, W, H, D, B}; out-of-bounds elements are
-// zero-filled by the TMA unit = the conv's zero padding, in all three spatial dimensions)
-// instead of 180-1440 16-byte cp.async per slice issued by four producer warps.  The brick
+// The GEMM: M = 128 voxels = 8(w) x 16(h) of one depth slice, K = Cin per tap, N = 3 x GW (the
+// three kd taps share one A operand: an input slice feeds up to three output slices in ONE
+// MMA).  The input brick of a depth slice (18 x 10 voxels with halo, up to 32 channels) is
+// brought in by ONE TMA tiled load (cp.async.bulk.tensor.5d over x viewed as {C, W, H, D, B};
+// out-of-bounds elements are zero-filled by the TMA unit = the conv's zero padding, in all
+// three spatial dimensions) -- the first generation of this kernel issued 180-1440 16-byte
+// cp.async per slice from four producer warps and was bound by them.  The brick
 // is voxel-major [18][10][CB] with the TMA swizzle matching the row size (CB*4 = 128/64/32
 // bytes -> SWIZZLE_128B/64B/32B); the A operand of tap (kh,kw) is a SHIFTED VIEW of it:
 // descriptor start = brick + (kh*10 + kw)*rowbytes (+32 B per K=8 step), stride between

@@ -1,8 +1,21 @@
 // K2 (tensor-core variant, TMA producer, part 2) — the stride-2 convolutions (conv1, conv3,
 // conv5) and the transposed convolutions (conv7, conv9, conv11) of CostRegNet on tcgen05.
-// Same GEMMs as conv3d_tc2.cu (see its header for the MODE_S2 / MODE_T column layouts); what
-// changes is how the input gets to shared memory and how the CTAs are scheduled:
-//   * one or two TMA tiled loads per input slice instead of 600-2400 16-byte cp.async;
+// The GEMMs ("resident brick + shifted-view UMMA descriptors", see conv3d_tma.cu):
+//   MODE_S2 (stride 2): M = 8(w) x 16(h) OUTPUT voxels of one output slice od.  Input row
+//     ih = 2*oh + kh - 1 => consecutive GEMM row groups are two brick rows apart; input column
+//     iw = 2*ow + kw - 1 => even and odd columns are separate planes so that 8 consecutive ow are
+//     again adjacent.  Odd input slices (s = 2a+1) feed outputs a (kd=2) and a+1 (kd=0) in ONE
+//     MMA of N = 2*GW; even slices feed output a (kd=1).
+//   MODE_T (transposed, output = 2x input): M = 8 x 16 INPUT voxels j of one input slice.
+//     Output voxel o = 2j + p (p in {0,1}^3, 8 parity classes); class p reads input j + s with
+//     tap k:  p=0 -> (s=0,k=1);  p=1 -> (s=0,k=2) and (s=1,k=0).  For each of the 4 in-plane
+//     shifts (sh,sw) the A view is shared by every (class, kd) it reaches, so one MMA of
+//     N = 12*Cout covers [kd=0 -> slice jd-1, pd=1 classes | kd=1 -> slice jd, pd=0 | kd=2 ->
+//     slice jd, pd=1] with zero weight rows for unreachable classes (the MMA count, not N, is
+//     what costs at these sizes: profiles/microbench/umma_rate.cu).
+// How the input gets to shared memory and how the CTAs are scheduled:
+//   * one or two TMA tiled loads per input slice (the first, cp.async generation of this kernel
+//     issued 600-2400 16-byte copies per slice and was producer-bound);
 //     out-of-bounds elements are zero-filled by the TMA unit (= the zero padding);
 //   * the brick is voxel-major [rows][9 columns][CB channels], swizzled by its row size, and
 //     every tap is a shifted view of it (start address + rows*9 + column, see conv3d_tma.cu);
@@ -386,7 +399,7 @@ conv3d_tma2_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   }
 }
 
-// B operand image [chunk][tap][cq][row][4], tf32-rounded: identical to conv3d_tc2.cu's
+// B operand image [chunk][tap][cq][row][4], tf32-rounded
 template <int MODE, int CIN, int COUT>
 __global__ void build_image_tma2_kernel(const float* __restrict__ wpk, float* __restrict__ img,
                                         int cout_total) {
