@@ -306,6 +306,47 @@ def run_sharded_config(name, rank, world, dev, precision, reps=3):
             "collective": "one all_gather_into_tensor per output key at the end (depth_0, confidence_2)"}
 
 
+OTHER_CONFIGS = {
+    # single-GPU timings of the remaining BASELINE.json configs (one reference view each); their
+    # parity against the oracle is in tests/test_gpu_cascade.py::test_full_size_parity_vs_oracle
+    "cfg3": dict(W=640, H=512, V=3, G=8, n_depths=(8, 32, 48)),
+    "cfg4_view": dict(W=1152, H=864, V=5, G=1, n_depths=(8, 32, 48)),
+    "cfg5_view": dict(W=1920, H=1056, V=7, G=1, n_depths=(8, 32, 64)),
+}
+
+
+def run_other_configs(dev, precision, reps=20):
+    import torch
+    from casmvsnet_pl_b200 import ABN, synth
+    from casmvsnet_pl_b200.graph import GraphedCascade
+    from casmvsnet_pl_b200.models.mvsnet import CascadeMVSNet
+    out = {}
+    for name, c in OTHER_CONFIGS.items():
+        torch.manual_seed(0)
+        model = CascadeMVSNet(n_depths=list(c["n_depths"]), num_groups=c["G"], norm_act=ABN,
+                              precision=precision)
+        synth.randomize_model_(model, 0)
+        model = model.eval().to(dev).requires_grad_(False)
+        imgs, pm, dmin, dint = synth.make_inputs(B=1, V=c["V"], W=c["W"], H=c["H"], seed=0)
+        g = GraphedCascade(model, imgs.to(dev), pm.to(dev), dmin, dint, warmup=2)
+        for _ in range(3):
+            g()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"config": f"{c['W']}x{c['H']}, V={c['V']}, G={c['G']}, "
+                               f"D={'/'.join(map(str, c['n_depths'][::-1]))}, one reference view",
+                     "ms_per_view": ms, "views_per_s": 1e3 / ms, "how": "CUDA-graph replay, inputs resident"}
+        del g, model
+        torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -630,6 +671,13 @@ def main():
             extras_failed["cpu_baseline_parity"] = f"{type(e).__name__}: {e}"[:300]
             print(f"WARNING: bench extra 'cpu_baseline_parity' failed: {e}", file=sys.stderr)
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            other = run_other_configs(dev, args.precision)
+        except Exception as e:                                       # noqa: BLE001
+            extras_failed["other_configs"] = f"{type(e).__name__}: {e}"[:300]
+
     pipelined = pipe is not None
     sharded = None
     if world > 1 and not args.no_sharded_configs:
@@ -677,6 +725,7 @@ def main():
             "parity": parity,
             "extras_failed": extras_failed or None,
             "sharded_configs": sharded,
+            "other_configs": other,
             "fallbacks": fallbacks,
             "sustained": sustained,
             "roofline_k2": roofline_k2,
