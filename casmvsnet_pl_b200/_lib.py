@@ -27,6 +27,7 @@ SIGNATURES = {
     "casmvs_release_weight_images": (c_int, [c_void_p, c_size_t]),
     "casmvs_weight_cache_generation": (c_uint64, []),
     "casmvs_weight_image_count": (c_int, [c_void_p, c_size_t]),
+    "casmvs_settle_weight_images": (c_int, []),
     "casmvs_warp_cost_workspace_bytes": (c_size_t, [c_int] * 6),
     "casmvs_warp_cost_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                      c_int, c_int, c_int, c_int, c_int, c_int, c_int,

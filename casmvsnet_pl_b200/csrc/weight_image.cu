@@ -65,10 +65,23 @@ static std::vector<CacheEntry> g_cache;
 static std::mutex g_cache_mu;
 static std::atomic<uint64_t> g_generation{0};
 
+// cudaEventQuery / cudaStreamWaitEvent on an event from outside a capture are "unsafe" calls that
+// INVALIDATE a stream capture (torch captures in global mode): while `st` is capturing the cache
+// touches no event.  An image that is not known to be built then relies on the caller having
+// synchronised between its warm-up and the capture -- GraphedCascade does, and marks everything
+// built with casmvs_settle_weight_images() -- and is used without programmatic dependent launch.
+static bool is_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs != cudaStreamCaptureStatusNone;
+}
+
 ImageRef image_cache_get(const void* wpk, int tag, size_t bytes, cudaStream_t st) {
   std::lock_guard<std::mutex> lock(g_cache_mu);
+  const bool capturing = is_capturing(st);
   for (auto& e : g_cache) {
     if (e.key != wpk || e.tag != tag || e.bytes != bytes) continue;
+    if (capturing) return ImageRef{e.img, true, e.settled};
     if (!e.settled && e.built && cudaEventQuery(e.built) == cudaSuccess) e.settled = true;
     if (!e.settled && e.built && e.built_on != st) {
       // built on another stream and possibly still running there: order this stream after it
@@ -95,6 +108,7 @@ void image_cache_built(const float* img, cudaStream_t st) {
   for (auto& e : g_cache) {
     if (e.img != img) continue;
     e.built_on = st;
+    if (is_capturing(st)) return;      // built inside a capture: never marked settled (no PDL)
     if (!e.built) cudaEventCreateWithFlags(&e.built, cudaEventDisableTiming);
     if (e.built && cudaEventRecord(e.built, st) != cudaSuccess) {
       cudaGetLastError();          // e.g. a capturing stream: leave the entry unsettled
@@ -142,6 +156,17 @@ extern "C" int casmvs_invalidate_weight_cache(void) {
 }
 
 extern "C" uint64_t casmvs_weight_cache_generation(void) { return tc::g_generation.load(); }
+
+extern "C" int casmvs_settle_weight_images(void) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    set_error("settle_weight_images: %s", cudaGetErrorString(e));
+    return -2;
+  }
+  std::lock_guard<std::mutex> lock(tc::g_cache_mu);
+  for (auto& en : tc::g_cache) en.settled = true;      // every builder enqueued so far has finished
+  return 0;
+}
 
 extern "C" int casmvs_weight_image_count(const void* w_packed, size_t bytes) {
   std::lock_guard<std::mutex> lock(tc::g_cache_mu);

@@ -32,6 +32,9 @@ class GraphedCascade:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         from . import _lib
+        # the capture below must not touch the operand-image builders' events: tell the library
+        # that everything the warm-up built is complete
+        _lib.check(_lib.load().casmvs_settle_weight_images(), "settle_weight_images")
         n0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self.graph):

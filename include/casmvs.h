@@ -139,6 +139,10 @@ uint64_t casmvs_weight_cache_generation(void);
  * it per packed buffer it depends on and re-checks it before every replay (a release anywhere
  * else -- another model, a dead model's recycled address -- does not invalidate the graph). */
 int casmvs_weight_image_count(const void* w_packed, size_t bytes);
+/* Synchronises the device and marks every cached image as built.  Call it between the warm-up
+ * forward and a CUDA-graph capture: during a capture the cache cannot query or wait on the
+ * builders' events (such calls invalidate the capture), so it must already know. */
+int casmvs_settle_weight_images(void);
 int casmvs_conv3d_fwd(const float* x, const float* w_packed, const float* scale,
                       const float* shift, float slope, const float* skip, float* y,
                       int B, int Cin, int Cout, int D, int h, int w, /* INPUT dims */
