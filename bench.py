@@ -7,13 +7,23 @@ A *step* is one `CascadeMVSNet.forward` (FeatureNet + three cascade stages) over
 one batch of synthetic DTU-shaped views per GPU: BASELINE.json configs[1] —
 640x512, V=3, D=48/32/8, variance cost, B=1 per GPU.  Metric: depth-maps/sec.
 
-  value     : whole-job depth-maps/s, inputs resident in HBM when timing starts
-  e2e       : same through the public API with HOST (pinned) inputs; H2D copy of
-              imgs+proj and D2H read of depth_0 + confidence_2 inside the timed region
-  roofline  : the fused warp+variance kernel (K1): algorithmic bytes of its three
-              launches / their CUDA-event time, vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline : the CPU oracle port of the reference path on this box's host cores
-  --impl reference : the reference arm = the same CPU port, all host threads
+  value        whole-job depth-maps/s, inputs resident in HBM when timing starts (CUDA-graph
+               replay; at N > 1 every rank keeps its K depth maps and the ranks gather them ONCE,
+               inside the timed region)
+  e2e          the same through the public API with HOST (pinned) inputs: H2D copy of imgs+proj and
+               D2H read of depth_0 + confidence_2 every step, inside the timed region (2-slot
+               pipeline on every rank)
+  roofline     the fused warp+variance kernel (K1): algorithmic bytes of its three launches /
+               their CUDA-event time (L2 flushed), vs MEASURED_PEAKS.json hbm_gbs
+  roofline_k2  the three CostRegNet stacks: ms, GB/s, TFLOP/s, tensor-pipe % (from profiles/)
+  parity       this run's GPU output vs the oracle on the same inputs and weights (N = 1)
+  sustained    >= 2 s of back-to-back replays with clocks / power sampled
+  fallbacks    tf32 layers that ran on the CUDA-core fallback kernel (must be 0)
+  other_configs    single-view graph-replay timings of cfg3 / cfg4 / cfg5 (N = 1)
+  sharded_configs  cfg4 (batch of N views) and cfg5 (batch of 4N) sharded over the N ranks with one
+                   all_gather at the end: ms per batch, bit-equality with one GPU (N > 1)
+  cpu_baseline the CPU oracle port of the reference path on this box's host cores (N = 1)
+  --impl reference : the reference arm = the same CPU port, fastest thread count
 """
 import argparse
 import json
