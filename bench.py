@@ -488,6 +488,7 @@ def main():
     launches = _lib.launch_count() - n0
     if graphed is not None:      # graph replays launch the captured libcasmvs kernels
         launches += graphed.kernels_per_replay * K
+    run_e2e(max(3, args.warmup))     # copy engines / PCIe links idled during the resident timing
     ms_e2e = timed(run_e2e, K)
     clocks = sampler.stop() if sampler else None
 
