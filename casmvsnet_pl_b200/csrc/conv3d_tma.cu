@@ -57,10 +57,17 @@ struct Params {
   int planar;           // 1x3x3 kernel: input slice s feeds output slice s only (kd = 1)
   long long* dbg;       // optional timeline of CTA 0: [role][slice][4] clock64 stamps
 };
+// per-role clock64 timeline of CTA 0 (profiles/tc_timeline.py): compiled in only with
+// `make TIMELINE=1` -- each stamp costs ~6 instructions in loops whose roles are bound by
+// their own scalar instruction stream (profiles/r2_k2_n8_stalls.txt)
+#ifdef CASMVS_TIMELINE
 #define TMA_STAMP(role, idx, k)                                                                 \
   do {                                                                                          \
     if (p.dbg && blockIdx.x == 0 && (idx) < 64) p.dbg[((role) * 64 + (idx)) * 4 + (k)] = clock64(); \
   } while (0)
+#else
+#define TMA_STAMP(role, idx, k) do { } while (0)
+#endif
 
 template <int CIN, int GW, int SLOTS_>
 struct Smem {

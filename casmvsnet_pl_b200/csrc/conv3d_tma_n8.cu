@@ -25,6 +25,8 @@
 // tfull/tempty accumulator barriers.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "tma_common.cuh"
@@ -56,12 +58,20 @@ struct Params {
   int tiles_w, tiles_h, nchunks, dchunk;
   int round_out;
   int planar;          // 1x3x3 kernel: input slice s feeds output slice s only (kd = 1)
+  FastDiv fd_tw, fd_th, fd_ck;   // item -> (tile column, tile row, depth chunk, batch)
   long long* dbg;
 };
+// per-role clock64 timeline of CTA 0 (profiles/tc_timeline.py): compiled in only with
+// `make TIMELINE=1` -- each stamp costs ~6 instructions in loops whose roles are bound by
+// their own scalar instruction stream (profiles/r2_k2_n8_stalls.txt)
+#ifdef CASMVS_TIMELINE
 #define N8_STAMP(role, idx, k)                                                                  \
   do {                                                                                          \
     if (p.dbg && blockIdx.x == 0 && (idx) < 64) p.dbg[((role) * 64 + (idx)) * 4 + (k)] = clock64(); \
   } while (0)
+#else
+#define N8_STAMP(role, idx, k) do { } while (0)
+#endif
 
 template <int CIN, int SLOTS_>
 struct Smem {
@@ -99,6 +109,120 @@ __device__ __forceinline__ void tmem_ld_wait(float (&v)[8]) {
                  "+f"(v[6]), "+f"(v[7])
                :: "memory");
 }
+// one wait for the three loads of an output slice
+__device__ __forceinline__ void tmem_ld_wait3(float (&a)[8], float (&b)[8], float (&c)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]),
+                 "+f"(a[6]), "+f"(a[7]), "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]),
+                 "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7]), "+f"(c[0]), "+f"(c[1]),
+                 "+f"(c[2]), "+f"(c[3]), "+f"(c[4]), "+f"(c[5]), "+f"(c[6]), "+f"(c[7])
+               :: "memory");
+}
+// the three kw groups of one output slice (columns +0, +8, +16) in one statement: one address
+// register, one wait
+__device__ __forceinline__ void tmem_ld3x8(uint32_t taddr, float (&a)[8], float (&b)[8],
+                                           float (&c)[8]) {
+  uint32_t r[24];
+  asm volatile(
+      "{\n\t.reg .b32 t1, t2;\n\t"
+      "add.u32 t1, %24, 8;\n\t"
+      "add.u32 t2, %24, 16;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%24];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%8,%9,%10,%11,%12,%13,%14,%15}, [t1];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%16,%17,%18,%19,%20,%21,%22,%23}, [t2];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t}"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a[i] = __uint_as_float(r[i]);
+    b[i] = __uint_as_float(r[8 + i]);
+    c[i] = __uint_as_float(r[16 + i]);
+  }
+}
+__device__ __forceinline__ void tmem_zero3x8(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "{\n\t.reg .b32 t1, t2;\n\t"
+      "add.u32 t1, %0, 8;\n\t"
+      "add.u32 t2, %0, 16;\n\t"
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};\n\t"
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [t1], {%1,%1,%1,%1,%1,%1,%1,%1};\n\t"
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [t2], {%1,%1,%1,%1,%1,%1,%1,%1};\n\t"
+      "tcgen05.wait::st.sync.aligned;\n\t}"
+      ::"r"(taddr), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld3x1(uint32_t taddr, float& a, float& b, float& c) {
+  uint32_t r0, r1, r2;
+  asm volatile(
+      "{\n\t.reg .b32 t1, t2;\n\t"
+      "add.u32 t1, %3, 8;\n\t"
+      "add.u32 t2, %3, 16;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%3];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%1}, [t1];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x1.b32 {%2}, [t2];\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t}"
+      : "=r"(r0), "=r"(r1), "=r"(r2)
+      : "r"(taddr)
+      : "memory");
+  a = __uint_as_float(r0); b = __uint_as_float(r1); c = __uint_as_float(r2);
+}
+__device__ __forceinline__ void tmem_zero3x1(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile(
+      "{\n\t.reg .b32 t1, t2;\n\t"
+      "add.u32 t1, %0, 8;\n\t"
+      "add.u32 t2, %0, 16;\n\t"
+      "tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};\n\t"
+      "tcgen05.st.sync.aligned.32x32b.x1.b32 [t1], {%1};\n\t"
+      "tcgen05.st.sync.aligned.32x32b.x1.b32 [t2], {%1};\n\t"
+      "tcgen05.wait::st.sync.aligned;\n\t}"
+      ::"r"(taddr), "r"(z)
+      : "memory");
+}
+// single-column variants (Cout = 1: only channel 0 of each kw group is ever non-zero)
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tmem_ld_wait1x3(float& a, float& b, float& c) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a), "+f"(b), "+f"(c)::"memory");
+}
+__device__ __forceinline__ void tmem_zero1(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(z) : "memory");
+}
+// round to tf32, to nearest with ties away (== cvt.rna.tf32.f32 for every finite input and inf;
+// the compiler expands the cvt into this plus an inf/NaN guard)
+__device__ __forceinline__ float round_tf32_bits(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b,
+                                                   unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 __device__ __forceinline__ void tmem_zero8(uint32_t taddr) {
   const uint32_t z = 0u;
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};"
@@ -106,7 +230,12 @@ __device__ __forceinline__ void tmem_zero8(uint32_t taddr) {
                : "memory");
 }
 
-template <int CIN, int SLOTS_, int SETS>
+// CO: output channels known at compile time (8: conv0 and the planar FeatureNet layers, 1: the
+// prob head), 0 = any Cout <= 8 (per-channel stores).  The kernel is bound by its own scalar
+// instruction stream (0.6 instructions per cycle and scheduler at four CTAs per SM,
+// profiles/r2_k2_n8_stalls.txt), 57 % of it in the epilogue warps: the specialisations exist to
+// shorten that stream.
+template <int CIN, int SLOTS_, int SETS, int CO>
 __global__ void __launch_bounds__((4 * SETS + 2) * 32, 1)
 conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   using S = Smem<CIN, SLOTS_>;
@@ -169,11 +298,10 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   uint32_t gs = 0;                                  // slices processed before this item (all roles)
   int ep = 0;                                       // items processed by this CTA
   for (int item0 = blockIdx.x; item0 < total_items; item0 += gridDim.x, ++ep) {
-    int item = item0;
-    const int tw = item % p.tiles_w; item /= p.tiles_w;
-    const int th = item % p.tiles_h; item /= p.tiles_h;
-    const int ck = item % p.nchunks;
-    const int b = item / p.nchunks;
+    uint32_t utw, uth, uck;
+    const int b = (int)fastdivmod(
+        fastdivmod(fastdivmod((uint32_t)item0, p.fd_tw, utw), p.fd_th, uth), p.fd_ck, uck);
+    const int tw = (int)utw, th = (int)uth, ck = (int)uck;
     const int w0 = tw * kColsOut, h0 = th * kRowsOut;
     const int d0 = ck * p.dchunk, d1 = min(p.D, d0 + p.dchunk);
     const int nd = d1 - d0;
@@ -259,66 +387,89 @@ conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
       const int oh = h0 + q, ow = w0 + lane;
       const bool writes = lane < kColsOut && oh < p.H && ow < p.W;
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-      for (int j = set; j < p.dchunk; j += SETS) {
+      // this lane's voxel in output slice d0; one slice further = slice_stride floats
+      const size_t o0 = ((((size_t)b * p.D + d0) * p.H + oh) * p.W + ow) * p.Cout;
+      const size_t slice_stride = (size_t)p.H * p.W * p.Cout;
+      size_t o = o0 + (size_t)set * slice_stride;
+      for (int j = set; j < p.dchunk; j += SETS, o += SETS * slice_stride) {
         if (threadIdx.x == 0) N8_STAMP(2, ep * p.dchunk + j, 0);
         mbar_wait(bar_tfull + 8 * j, ep & 1);
         if (threadIdx.x == 0) N8_STAMP(2, ep * p.dchunk + j, 1);
         tc_fence_after();
+        const uint32_t tg = lane_base + j * kG;
         if (j >= nd) {
           // unused group: only its first 8 columns can have been written (pad columns of the
           // last slice's MMA, non-zero weights) -- clean them for the next item
           if (j == nd) {
-            tmem_zero8(lane_base + j * kG);
+            tmem_zero8(tg);
             tmem_wait_st();
             tc_fence_before();
           }
           mbar_arrive(bar_tempty + 8 * j);
           continue;
         }
-        float a0[8], a1[8], a2[8];
-        tmem_ld8(lane_base + j * kG, a0);
-        tmem_ld8(lane_base + j * kG + 8, a1);
-        tmem_ld8(lane_base + j * kG + 16, a2);
-        tmem_ld_wait(a0);
-        tmem_ld_wait(a1);
-        tmem_ld_wait(a2);
-        tmem_zero8(lane_base + j * kG);
-        tmem_zero8(lane_base + j * kG + 8);
-        tmem_zero8(lane_base + j * kG + 16);
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(bar_tempty + 8 * j);           // group j drained and zero again
-        if (threadIdx.x == 0) N8_STAMP(2, ep * p.dchunk + j, 2);
-        // out[c] = D_kw0[c] + D_kw1[c+1] + D_kw2[c+2]   (c = brick column = lane)
-        float v[8];
+        if constexpr (CO == 1) {
+          // channel 0 of the three kw groups; every other column of the group only ever
+          // accumulates x * 0 (zero rows of the operand image) and is never read
+          float a0, a1, a2;
+          tmem_ld3x1(tg, a0, a1, a2);
+          tmem_zero3x1(tg);
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8 * j);         // group j drained and zero again
+          if (threadIdx.x == 0) N8_STAMP(2, ep * p.dchunk + j, 2);
+          const float s1 = __shfl_down_sync(0xffffffffu, a1, 1);
+          const float s2 = __shfl_down_sync(0xffffffffu, a2, 2);
+          float t = fmaf(a0 + s1 + s2, s_param[0], s_param[8]);
+          t = t >= 0.f ? t : t * p.slope;
+          if (writes) {
+            if (p.skip) t += __ldg(p.skip + o);
+            p.y[o] = p.round_out ? round_tf32_bits(t) : t;
+          }
+        } else {
+          float a0[8], a1[8], a2[8];
+          tmem_ld3x8(tg, a0, a1, a2);
+          tmem_zero3x8(tg);
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8 * j);         // group j drained and zero again
+          if (threadIdx.x == 0) N8_STAMP(2, ep * p.dchunk + j, 2);
+          // out[c] = D_kw0[c] + D_kw1[c+1] + D_kw2[c+2]   (c = brick column = lane), as packed
+          // pairs of channels (add.f32x2 / fma.f32x2: the same IEEE operations, half the issues)
+          float v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float s1 = __shfl_down_sync(0xffffffffu, a1[k], 1);
-          const float s2 = __shfl_down_sync(0xffffffffu, a2[k], 2);
-          const float t = fmaf(a0[k] + s1 + s2, s_param[k], s_param[8 + k]);
-          v[k] = t >= 0.f ? t : t * p.slope;
-        }
-        if (writes) {
-          const size_t o = ((((size_t)b * p.D + (d0 + j)) * p.H + oh) * p.W + ow) * p.Cout;
-          if (p.Cout == 8) {
-            if (p.skip) {
-              const float4 s0 = ldg4(p.skip + o), s1 = ldg4(p.skip + o + 4);
-              v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
-              v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
-            }
-            if (p.round_out) {
+          for (int k = 0; k < 8; k += 2) {
+            const float s1a = __shfl_down_sync(0xffffffffu, a1[k], 1);
+            const float s1b = __shfl_down_sync(0xffffffffu, a1[k + 1], 1);
+            const float s2a = __shfl_down_sync(0xffffffffu, a2[k], 2);
+            const float s2b = __shfl_down_sync(0xffffffffu, a2[k + 1], 2);
+            const unsigned long long t2 =
+                fma2(add2(add2(pk2(a0[k], a0[k + 1]), pk2(s1a, s1b)), pk2(s2a, s2b)),
+                     pk2(s_param[k], s_param[k + 1]), pk2(s_param[8 + k], s_param[9 + k]));
+            float ta, tb;
+            unpk2(t2, ta, tb);
+            v[k] = ta >= 0.f ? ta : ta * p.slope;
+            v[k + 1] = tb >= 0.f ? tb : tb * p.slope;
+          }
+          if (writes) {
+            if constexpr (CO == 8) {
+              if (p.skip) {
+                const float4 s0 = ldg4(p.skip + o), s1 = ldg4(p.skip + o + 4);
+                v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w;
+                v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+              }
+              if (p.round_out) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) v[k] = to_tf32(v[k]);
-            }
-            st4(p.y + o, make_float4(v[0], v[1], v[2], v[3]));
-            st4(p.y + o + 4, make_float4(v[4], v[5], v[6], v[7]));
-          } else {
+                for (int k = 0; k < 8; ++k) v[k] = round_tf32_bits(v[k]);
+              }
+              st4(p.y + o, make_float4(v[0], v[1], v[2], v[3]));
+              st4(p.y + o + 4, make_float4(v[4], v[5], v[6], v[7]));
+            } else {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              if (k < p.Cout) {
-                float tt = v[k];
-                if (p.skip) tt += __ldg(p.skip + o + k);
-                p.y[o + k] = p.round_out ? to_tf32(tt) : tt;
+              for (int k = 0; k < 8; ++k) {
+                if (k < p.Cout) {
+                  float tt = v[k];
+                  if (p.skip) tt += __ldg(p.skip + o + k);
+                  p.y[o + k] = p.round_out ? round_tf32_bits(tt) : tt;
+                }
               }
             }
           }
@@ -360,11 +511,11 @@ __global__ void build_image_n8_kernel(const float* __restrict__ wpk, float* __re
   }
 }
 
-template <int CIN, int SLOTS, int SETS>
-static int launch8(const float* x, const float* wpk, Params p, cudaStream_t st) {
+template <int CIN, int SLOTS, int SETS, int CO>
+static int launch8co(const float* x, const float* wpk, Params p, cudaStream_t st) {
   using S = Smem<CIN, SLOTS>;
   constexpr int kThreads8 = (4 * SETS + 2) * 32;
-  auto kfn = conv3d_tma_n8_kernel<CIN, SLOTS, SETS>;
+  auto kfn = conv3d_tma_n8_kernel<CIN, SLOTS, SETS, CO>;
   static std::atomic<bool> attr_set[kMaxDevices];
   if (int rc = opt_in_smem(kfn, S::kTotal, attr_set, "conv3d_tma_n8")) return rc;
   const CUtensorMap* map = tma::input_map(x, p.B, p.D, p.H, p.W, CIN, CIN, kBW, kBH);
@@ -414,10 +565,22 @@ static int launch8(const float* x, const float* wpk, Params p, cudaStream_t st) 
   }
   p.bimg = img;
   const long items = (long)p.B * p.nchunks * p.tiles_h * p.tiles_w;
+  const uint32_t dmax = (uint32_t)std::max(p.tiles_w, std::max(p.tiles_h, p.nchunks));
+  if (!fastdiv_ok((uint64_t)items, dmax)) return 1;          // left to the other kernels
+  p.fd_tw = make_fastdiv((uint32_t)p.tiles_w);
+  p.fd_th = make_fastdiv((uint32_t)p.tiles_h);
+  p.fd_ck = make_fastdiv((uint32_t)p.nchunks);
   const long resident = (long)num_sms() * per_sm;
   const long gx = items < resident ? items : resident;
   tma::launch_pdl(ir.settled, kfn, dim3((unsigned)gx), kThreads8, S::kTotal, st, *map, p);
   return after_launch("conv3d_tma_n8");
+}
+
+template <int CIN, int SLOTS, int SETS>
+static int launch8(const float* x, const float* wpk, const Params& p, cudaStream_t st) {
+  if (p.Cout == 8) return launch8co<CIN, SLOTS, SETS, 8>(x, wpk, p, st);
+  if (p.Cout == 1) return launch8co<CIN, SLOTS, SETS, 1>(x, wpk, p, st);
+  return launch8co<CIN, SLOTS, SETS, 0>(x, wpk, p, st);
 }
 
 }  // namespace tma8
