@@ -609,16 +609,16 @@ int conv3d_tma_n8(const float* x, const float* wpk, const float* scale, const fl
   p.planar = kind == CASMVS_CONV_PLANAR ? 1 : 0;
   // the prob head feeds the softmax: keep fp32; callers can ask for unrounded outputs
   p.round_out = (round_out && Cout > 1 && !(precision_flags & CASMVS_KEEP_FP32_OUT)) ? 1 : 0;
-  static int sets = -1;
-  if (sets < 0) {
-    const char* e = getenv("CASMVS_N8_SETS");
-    sets = e ? atoi(e) : 1;
+  // second set of epilogue warps (alternate output slices): bit 0 -> Cin = 8, bit 1 -> Cin = 16,
+  // bit 2 -> Cin = 32 (CASMVS_N8_SETS2_MASK; measured per bit in profiles/r2_switch_ab.txt)
+  static int sets2 = -1;
+  if (sets2 < 0) {
+    const char* e = getenv("CASMVS_N8_SETS2_MASK");
+    sets2 = e ? atoi(e) : 1;     // cfg2 step: 1.0957 ms with 0, 1.0589 with 1, 1.0580 with 3, 1.0620 with 7 (three sets at Cin = 8: 1.1111)
   }
-  if (sets == 2) {
-    if (Cin == 8) return tma8::launch8<8, 4, 2>(x, wpk, p, st);
-    if (Cin == 16) return tma8::launch8<16, 4, 2>(x, wpk, p, st);
-    return tma8::launch8<32, 3, 2>(x, wpk, p, st);
-  }
+  if (Cin == 8 && (sets2 & 1)) return tma8::launch8<8, 4, 2>(x, wpk, p, st);
+  if (Cin == 16 && (sets2 & 2)) return tma8::launch8<16, 4, 2>(x, wpk, p, st);
+  if (Cin == 32 && (sets2 & 4)) return tma8::launch8<32, 3, 2>(x, wpk, p, st);
   static int slots8 = -1;
   if (slots8 < 0) {
     const char* e = getenv("CASMVS_N8_SLOTS8");       // ring depth of the Cin = 8 kernels (4 or 6)
