@@ -20,6 +20,9 @@ one batch of synthetic DTU-shaped views per GPU: BASELINE.json configs[1] —
   sustained    >= 2 s of back-to-back replays with clocks / power sampled
   fallbacks    tf32 layers that ran on the CUDA-core fallback kernel (must be 0)
   other_configs    single-view graph-replay timings of cfg3 / cfg4 / cfg5 (N = 1)
+  throughput_modes cfg2 depth maps/s when the caller gives the GPU more than one reference view at
+                   a time: a batch of 4 per forward, or 3 single-view graphs in flight on 3 streams
+                   (`value` stays one view at a time, the reference eval loop's batch size)
   sharded_configs  cfg4 (batch of N views) and cfg5 (batch of 4N) sharded over the N ranks with one
                    all_gather at the end: ms per batch, bit-equality with one GPU (N > 1)
   cpu_baseline the CPU oracle port of the reference path on this box's host cores (N = 1)
@@ -357,6 +360,50 @@ def run_other_configs(dev, precision, reps=20):
     return out
 
 
+def run_throughput_modes(model, dev, reps=30):
+    """cfg2 with more than one independent reference view on the GPU at once (inputs resident)."""
+    import torch
+    from casmvsnet_pl_b200 import synth
+    from casmvsnet_pl_b200.graph import GraphedCascade
+    out = {}
+    imgs, pm, dmin, dint = synth.make_inputs(B=1, V=VIEWS, W=W_IMG, H=H_IMG, seed=0)
+
+    def clock(fn, n_maps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_maps
+        return {"ms_per_depth_map": ms, "depth_maps_per_s": 1e3 / ms}
+
+    BATCH = 4
+    g = GraphedCascade(model, imgs.expand(BATCH, -1, -1, -1, -1).contiguous().to(dev),
+                       pm.expand(BATCH, *pm.shape[1:]).contiguous().to(dev), dmin, dint, warmup=2)
+    out["batch_of_4_per_forward"] = clock(lambda: [g() for _ in range(reps)], reps * BATCH)
+    del g
+    torch.cuda.empty_cache()
+    K = 3
+    gs = [GraphedCascade(model, imgs.to(dev), pm.to(dev), dmin, dint, warmup=1) for _ in range(K)]
+    streams = [torch.cuda.Stream() for _ in range(K)]
+
+    def in_flight():
+        main_s = torch.cuda.current_stream()
+        for s_ in streams:
+            s_.wait_stream(main_s)
+        for i in range(reps * K):
+            with torch.cuda.stream(streams[i % K]):
+                gs[i % K].graph.replay()
+        for s_ in streams:
+            main_s.wait_stream(s_)
+    out["3_single_view_graphs_in_flight"] = clock(in_flight, reps * K)
+    del gs
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -613,18 +660,27 @@ def main():
                     cost = ops.warp_cost(f, pm_d[:, :, l].contiguous(), dv, 1, ops.NHWC,
                                          round_tf32=(args.precision == "tf32"))
                     reg = getattr(model, f"cost_reg_{l}")
+                    # the 11 launches of a stack as ONE captured graph: launched eagerly from
+                    # Python the coarsest stack (0.19 ms of GPU work) is bound by the host
+                    for _ in range(2):
+                        reg(cost)
+                    torch.cuda.synchronize()
+                    _lib.check(_lib.load().casmvs_settle_weight_images(), "settle_weight_images")
+                    stack = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(stack):
+                        reg(cost)
                     ts = []
                     for it in range(3 + 10):
                         flush.zero_()
                         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         e0.record()
-                        reg(cost)
+                        stack.replay()
                         e1.record()
                         torch.cuda.synchronize()
                         if it >= 3:
                             ts.append(e0.elapsed_time(e1))
                     stage_ms.append(sum(ts) / len(ts))
-                    del cost
+                    del cost, stack
             k2_ms = sum(stage_ms)
             roofline_k2 = {"kernel": "CostRegNet x3 (33 tcgen05 conv launches / depth map)",
                            "algorithmic_bytes": K2_ALGO_BYTES, "flop": K2_ALGO_FLOP, "ms": k2_ms,
@@ -634,7 +690,7 @@ def main():
                            "TFLOPps": K2_ALGO_FLOP / (k2_ms * 1e-3) / 1e12,
                            "bound": "hbm (fp32 activations, Cout <= 64: 44 FLOP/B << ridge)",
                            "tensor_pipe_pct": None,
-                           "l2": "flushed before every timed stack"}
+                           "l2": "flushed before every timed stack (each stack = one captured graph)"}
             prof = os.path.join(ROOT, "profiles", "k2_tensor_pipe.json")
             if os.path.isfile(prof):
                 try:
@@ -689,6 +745,13 @@ def main():
         except Exception as e:                                       # noqa: BLE001
             extras_failed["other_configs"] = f"{type(e).__name__}: {e}"[:300]
 
+    modes = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            modes = run_throughput_modes(model, dev)
+        except Exception as e:                                       # noqa: BLE001
+            extras_failed["throughput_modes"] = f"{type(e).__name__}: {e}"[:300]
+
     pipelined = pipe is not None
     sharded = None
     if world > 1 and not args.no_sharded_configs:
@@ -737,6 +800,7 @@ def main():
             "extras_failed": extras_failed or None,
             "sharded_configs": sharded,
             "other_configs": other,
+            "throughput_modes": modes,
             "fallbacks": fallbacks,
             "sustained": sustained,
             "roofline_k2": roofline_k2,

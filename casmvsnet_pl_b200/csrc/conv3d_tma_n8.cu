@@ -92,32 +92,6 @@ __host__ __device__ constexpr int tmem_cols_for8(int n) {
   return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512;
 }
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]),
-                 "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-// the loaded registers are only valid after the wait: tie them to it so that the compiler
-// cannot schedule a use above it
-__device__ __forceinline__ void tmem_ld_wait(float (&v)[8]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]),
-                 "+f"(v[6]), "+f"(v[7])
-               :: "memory");
-}
-// one wait for the three loads of an output slice
-__device__ __forceinline__ void tmem_ld_wait3(float (&a)[8], float (&b)[8], float (&c)[8]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+f"(a[0]), "+f"(a[1]), "+f"(a[2]), "+f"(a[3]), "+f"(a[4]), "+f"(a[5]),
-                 "+f"(a[6]), "+f"(a[7]), "+f"(b[0]), "+f"(b[1]), "+f"(b[2]), "+f"(b[3]),
-                 "+f"(b[4]), "+f"(b[5]), "+f"(b[6]), "+f"(b[7]), "+f"(c[0]), "+f"(c[1]),
-                 "+f"(c[2]), "+f"(c[3]), "+f"(c[4]), "+f"(c[5]), "+f"(c[6]), "+f"(c[7])
-               :: "memory");
-}
 // the three kw groups of one output slice (columns +0, +8, +16) in one statement: one address
 // register, one wait
 __device__ __forceinline__ void tmem_ld3x8(uint32_t taddr, float (&a)[8], float (&b)[8],
@@ -185,19 +159,6 @@ __device__ __forceinline__ void tmem_zero3x1(uint32_t taddr) {
       ::"r"(taddr), "r"(z)
       : "memory");
 }
-// single-column variants (Cout = 1: only channel 0 of each kw group is ever non-zero)
-__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
-  uint32_t r;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
-  return __uint_as_float(r);
-}
-__device__ __forceinline__ void tmem_ld_wait1x3(float& a, float& b, float& c) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+f"(a), "+f"(b), "+f"(c)::"memory");
-}
-__device__ __forceinline__ void tmem_zero1(uint32_t taddr) {
-  const uint32_t z = 0u;
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(z) : "memory");
-}
 // round to tf32, to nearest with ties away (== cvt.rna.tf32.f32 for every finite input and inf;
 // the compiler expands the cvt into this plus an inf/NaN guard)
 __device__ __forceinline__ float round_tf32_bits(float x) {
@@ -231,10 +192,12 @@ __device__ __forceinline__ void tmem_zero8(uint32_t taddr) {
 }
 
 // CO: output channels known at compile time (8: conv0 and the planar FeatureNet layers, 1: the
-// prob head), 0 = any Cout <= 8 (per-channel stores).  The kernel is bound by its own scalar
-// instruction stream (0.6 instructions per cycle and scheduler at four CTAs per SM,
-// profiles/r2_k2_n8_stalls.txt), 57 % of it in the epilogue warps: the specialisations exist to
-// shorten that stream.
+// prob head), 0 = any Cout <= 8 (per-channel stores).  The specialised epilogues are 120 (Cout 8:
+// packed add / fma pairs, 2-instruction tf32 rounding) and 50 (Cout 1: one TMEM column per kw
+// group) instructions per output slice instead of 160.  On their own they did not change the step
+// time -- the Cin = 8 layers are bound by the TMA brick-fetch rate, profiles/r2_k2_n8_stalls.txt --
+// but they are what made a second set of epilogue warps (SETS = 2) pay: the drain -> re-issue
+// round trip of an accumulator group shortens, 3.4 % of the cfg2 step.
 template <int CIN, int SLOTS_, int SETS, int CO>
 __global__ void __launch_bounds__((4 * SETS + 2) * 32, 1)
 conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
