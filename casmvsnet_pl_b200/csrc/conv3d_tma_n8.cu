@@ -199,7 +199,8 @@ __device__ __forceinline__ void tmem_zero8(uint32_t taddr) {
 // but they are what made a second set of epilogue warps (SETS = 2) pay: the drain -> re-issue
 // round trip of an accumulator group shortens, 3.4 % of the cfg2 step.
 template <int CIN, int SLOTS_, int SETS, int CO>
-__global__ void __launch_bounds__((4 * SETS + 2) * 32, 1)
+// two sets at Cin = 8: 320 threads; four resident CTAs need <= 51 registers (48 used, no spills)
+__global__ void __launch_bounds__((4 * SETS + 2) * 32, (SETS == 2 && CIN == 8) ? 4 : 1)
 conv3d_tma_n8_kernel(const __grid_constant__ CUtensorMap xmap, const Params p) {
   using S = Smem<CIN, SLOTS_>;
   constexpr int SLOTS = S::SLOTS;
