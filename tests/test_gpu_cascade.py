@@ -241,8 +241,8 @@ def test_feature_net_tensor_path_matches_fp32_path():
 
 
 def test_graph_and_pipeline_match_eager():
-    """CUDA-graph replay and the 2-slot host-buffer pipeline give bit-identical results to
-    eager calls (same kernels, same order per view)."""
+    """CUDA-graph replay and the host-buffer pipeline (views in flight on separate streams, or
+    serial compute) give bit-identical results to eager calls (same kernels per view)."""
     from casmvsnet_pl_b200.graph import GraphedCascade, PipelinedCascade
     model, _ = build(1, "tf32")
     views = [synth.make_inputs(B=1, V=3, W=160, H=128, seed=s) for s in (0, 1, 2, 3, 4)]
@@ -255,16 +255,20 @@ def test_graph_and_pipeline_match_eager():
     for (imgs, pm, _, _), (d, c) in zip(views, eager):
         r = g(imgs.to(DEV), pm.to(DEV))
         assert torch.equal(r["depth_0"].cpu(), d) and torch.equal(r["confidence_2"].cpu(), c)
-    pipe = PipelinedCascade(model, views[0][0].to(DEV), views[0][1].to(DEV), dmin, dint)
-    got = []
-    for imgs, pm, _, _ in views:
-        r = pipe.submit(imgs.pin_memory(), pm.pin_memory())
-        if r is not None:
-            got.append((r[0].clone(), r[1].clone()))
-    got += [(a.clone(), b.clone()) for a, b in pipe.drain()]
-    assert len(got) == len(views)
-    for (d, c), (gd, gc) in zip(eager, got):
-        assert torch.equal(gd, d) and torch.equal(gc, c)
+    # default: three slots, one compute stream per slot (consecutive views overlap on the GPU);
+    # and the serial-compute form with two slots
+    for kw in ({}, {"slots": 2, "concurrent": False}):
+        pipe = PipelinedCascade(model, views[0][0].to(DEV), views[0][1].to(DEV), dmin, dint, **kw)
+        got = []
+        for rnd in range(2):                        # second round: every slot is being re-used
+            for imgs, pm, _, _ in views:
+                r = pipe.submit(imgs.pin_memory(), pm.pin_memory())
+                if r is not None:
+                    got.append((r[0].clone(), r[1].clone()))
+        got += [(a.clone(), b.clone()) for a, b in pipe.drain()]
+        assert len(got) == 2 * len(views)
+        for (d, c), (gd, gc) in zip(eager + eager, got):
+            assert torch.equal(gd, d) and torch.equal(gc, c)
 
 
 def test_weight_image_lifetime_and_graph_generation():
