@@ -259,6 +259,12 @@ def test_graph_and_pipeline_match_eager():
     # and the serial-compute form with two slots
     for kw in ({}, {"slots": 2, "concurrent": False}):
         pipe = PipelinedCascade(model, views[0][0].to(DEV), views[0][1].to(DEV), dmin, dint, **kw)
+        # inputs resident in the slots' static buffers (bench.py `value`): every slot replays view 0
+        store = torch.empty(7, *eager[0][0].shape[1:], device=DEV)
+        last = pipe.run_resident(7, keep=lambda k: store[k:k + 1])
+        torch.cuda.synchronize()
+        assert torch.equal(last["depth_0"].cpu(), eager[0][0])
+        assert all(torch.equal(store[k:k + 1].cpu(), eager[0][0]) for k in range(7))
         got = []
         for rnd in range(2):                        # second round: every slot is being re-used
             for imgs, pm, _, _ in views:
