@@ -10,7 +10,8 @@ one batch of synthetic DTU-shaped views per GPU: BASELINE.json configs[1] —
   value        whole-job depth-maps/s, inputs resident in HBM when timing starts: K CUDA-graph
                replays through the streaming engine (PipelinedCascade: 3 slots, one compute stream
                each, so 3 independent reference views are in flight); at N > 1 every rank keeps its
-               K depth maps and the ranks gather them ONCE, inside the timed region
+               K depth maps and the ranks all-gather them inside the timed region, in chunks of 5
+               steps on a side stream while the next forwards run
   one_view_at_a_time  the same K replays strictly one after the other on one stream (the latency
                of a single depth map; rounds 1 and 2 reported this as `value` until the slots got
                their own streams)
@@ -470,13 +471,32 @@ def main():
         # each), one compute stream per slot -> consecutive views overlap each other on the GPU
         pipe = PipelinedCascade(model, imgs_d, pm_d, dmin, dint)
 
-    def gather_all(steps):
-        dist.all_gather_into_tensor(gathered[: world * steps * B], store[: steps * B])
+    # multi-GPU: the depth maps are gathered in chunks of GATHER_EVERY steps on a side stream while
+    # the next forwards run (the same single collective type, all_gather_into_tensor, issued as
+    # the results appear: at N = 8 a gather of 8 x 1.3 MB per step left to the end of the timed
+    # region costs ~0.1 ms per step, 10 % of the step)
+    GATHER_EVERY = 5
+    comm = torch.cuda.Stream() if world > 1 else None
+    works = []
+
+    def gather_chunk(k0, k1, events):
+        for ev in events:
+            comm.wait_event(ev)
+        with torch.cuda.stream(comm):
+            works.append(dist.all_gather_into_tensor(gathered[world * k0 * B: world * k1 * B],
+                                                     store[k0 * B: k1 * B], async_op=True))
+
+    def gather_finish():
+        while works:
+            works.pop(0).wait()                      # the current stream waits for the collective
+        torch.cuda.current_stream().wait_stream(comm)
 
     def run_resident(steps):
         """K forwards, inputs resident: through the streaming engine (3 views in flight)."""
         if pipe is not None:
-            res = pipe.run_resident(steps, keep=(lambda k: store[k * B:(k + 1) * B]) if world > 1 else None)
+            res = pipe.run_resident(steps, keep=(lambda k: store[k * B:(k + 1) * B]) if world > 1 else None,
+                                    every=GATHER_EVERY if world > 1 else 0,
+                                    on_chunk=gather_chunk if world > 1 else None)
         else:
             res = None
             with torch.no_grad():
@@ -484,8 +504,12 @@ def main():
                     res = model(imgs_d, pm_d, dmin, dint)
                     if world > 1:
                         store[k * B:(k + 1) * B].copy_(res["depth_0"])
+                        if (k + 1) % GATHER_EVERY == 0 or k + 1 == steps:
+                            ev = torch.cuda.Event()
+                            ev.record()
+                            gather_chunk(k + 1 - ((k % GATHER_EVERY) + 1), k + 1, [ev])
         if world > 1:
-            gather_all(steps)
+            gather_finish()
         return res
 
     def run_one_at_a_time(steps):
@@ -502,11 +526,16 @@ def main():
         if pipe is not None:
             # copies of neighbouring steps overlap the compute, and the (three) slots replay on
             # their own streams so that consecutive views overlap each other, on every rank
+            k0 = 0
             for k in range(steps):
                 pipe.submit(imgs_h, pm_h, keep=store[k * B:(k + 1) * B] if world > 1 else None)
+                if world > 1 and ((k + 1) % GATHER_EVERY == 0 or k + 1 == steps):
+                    gather_chunk(k0, k + 1, list(pipe.compute_done))
+                    k0 = k + 1
             pipe.drain()
         else:
             with torch.no_grad():
+                k0 = 0
                 for k in range(steps):
                     res = model(imgs_h.to(dev, non_blocking=True), pm_h.to(dev, non_blocking=True),
                                 dmin, dint)
@@ -515,8 +544,13 @@ def main():
                     out_depth_h.copy_(res["depth_0"], non_blocking=True)   # eval.py:224-226
                     out_conf_h.copy_(res["confidence_2"], non_blocking=True)
                     torch.cuda.current_stream().synchronize()
+                    if world > 1 and ((k + 1) % GATHER_EVERY == 0 or k + 1 == steps):
+                        ev = torch.cuda.Event()
+                        ev.record()
+                        gather_chunk(k0, k + 1, [ev])
+                        k0 = k + 1
         if world > 1:
-            gather_all(steps)
+            gather_finish()
 
     def barrier():
         if world > 1:
@@ -798,9 +832,10 @@ def main():
                                ("CascadeMVSNet.forward = FeatureNet (own kernels: planar tcgen05 "
                                 "convs, RGB block, FPN merges) + 3 cascade stages (K4, K1, K2 x 11 "
                                 "layers on tcgen05, K3)"),
-                       "parallelism": f"dp{world} (independent reference views per rank; ONE "
-                                      f"all_gather_into_tensor of all {args.steps} per-rank depth maps "
-                                      "at the end of the timed region)" if world > 1 else "single GPU",
+                       "parallelism": f"dp{world} (independent reference views per rank; the {args.steps} "
+                                      f"per-rank depth maps are gathered by all_gather_into_tensor in chunks of "
+                                      f"{GATHER_EVERY} steps on a side stream while the next forwards run, all "
+                                      "inside the timed region)" if world > 1 else "single GPU",
                        "numa": numa,
                        "precision": args.precision,
                        "cuda_graph": not args.no_graph,

@@ -157,13 +157,17 @@ class PipelinedCascade:
         self.n += 1
         return ret
 
-    def run_resident(self, steps, keep=None):
+    def run_resident(self, steps, keep=None, every=0, on_chunk=None):
         """`steps` forwards over the inputs already resident in the slots' static buffers (no host
         copies): slot k % slots replays on its own stream, the caller's stream joins them at the
-        end.  keep(k): optional device tensor that receives depth_0 of forward k."""
+        end.  keep(k): optional device tensor that receives depth_0 of forward k.
+        on_chunk(k0, k1, events): called after every `every` forwards (and after the last one) with
+        the events that complete forwards k0..k1-1 -- a multi-GPU caller starts the gather of that
+        chunk on a side stream while the next forwards run."""
         cur = torch.cuda.current_stream()
         for cs in self.compute:
             cs.wait_stream(cur)
+        k0 = 0
         for k in range(steps):
             i = k % len(self.slots)
             g = self.slots[i]
@@ -175,6 +179,9 @@ class PipelinedCascade:
                 if keep is not None:
                     keep(k).copy_(g.out["depth_0"])
             self.compute_done[i].record(self.compute[i])
+            if on_chunk is not None and every > 0 and ((k + 1) % every == 0 or k + 1 == steps):
+                on_chunk(k0, k + 1, list(self.compute_done))
+                k0 = k + 1
         for cs in self.compute:
             cur.wait_stream(cs)
         return self.slots[(steps - 1) % len(self.slots)].out if steps else None
