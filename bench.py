@@ -457,7 +457,8 @@ def main():
     imgs_h, pm_h = imgs_h.pin_memory(), pm_h.pin_memory()
     imgs_d, pm_d = imgs_h.to(dev), pm_h.to(dev)
     # multi-GPU: every rank keeps the depth maps of its own views on the device and the path's
-    # single collective gathers them ONCE, at the end of the timed region
+    # single collective type (all-gather of per-view depth maps) collects them
+    # inside the timed region, chunk by chunk (gather_chunk below)
     nkeep = max(K, args.warmup, 3)
     store = torch.empty(nkeep * B, H_IMG, W_IMG, device=dev) if world > 1 else None
     gathered = torch.empty(world * nkeep * B, H_IMG, W_IMG, device=dev) if world > 1 else None
