@@ -1,9 +1,19 @@
 """Per-layer timing of the Cout<=8 conv kernel (conv3d_tma_n8.cu) at the six cfg2 shapes, L2 flushed,
-CUDA events; arguments: CASMVS_N8_DCHUNK values to force (0 = the library's own choice).
+CUDA events; arguments: CASMVS_N8_DCHUNK caps to apply (0 = the library's own choice).  The library
+reads the variable once per process, so every value runs in its own child process.
 
     python profiles/bench_n8.py 0 4 8
 """
-import os, sys, torch
+import os, subprocess, sys
+if len(sys.argv) > 2:
+    for c in sys.argv[1:]:
+        env = dict(os.environ)
+        env.pop("CASMVS_N8_DCHUNK", None)
+        if int(c):
+            env["CASMVS_N8_DCHUNK"] = c
+        subprocess.run([sys.executable, os.path.abspath(__file__), c], env=env, check=True)
+    sys.exit(0)
+import torch
 torch.set_grad_enabled(False)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -22,8 +32,6 @@ for name, cin, cout, dims in shapes:
     sc = torch.ones(cout, device=dev); sh = torch.zeros(cout, device=dev)
     row = []
     for c in chunks:
-        if c: os.environ["CASMVS_N8_DCHUNK"] = str(c)
-        else: os.environ.pop("CASMVS_N8_DCHUNK", None)
         ts = []
         for it in range(13):
             flush.zero_()
