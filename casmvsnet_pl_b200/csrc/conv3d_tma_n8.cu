@@ -19,10 +19,12 @@
 //     D[c][kw=0] + D[c+1][kw=1] + D[c+2][kw=2], i.e. a shift of 1 and 2 TMEM lanes INSIDE one
 //     warp (a warp owns one image row of 32 brick columns): two __shfl_down per value, no
 //     shared memory and no cross-warp barrier.  30 of the 32 brick columns produce outputs.
-// Everything else is as in conv3d_tma.cu: persistent CTAs, 6 warps (0-3 epilogue, 4 TMA
-// producer, 5 MMA issuer), linear TMEM accumulators (24 columns per output slice) that every
-// MMA accumulates into and the epilogue re-zeroes after reading, full/empty ring barriers and
-// tfull/tempty accumulator barriers.
+// Everything else is as in conv3d_tma.cu: persistent CTAs, 4 x SETS epilogue warps + TMA
+// producer + MMA issuer (SETS = 2 at Cin = 8: the two sets drain alternate output slices),
+// linear TMEM accumulators (24 columns per output slice) that every MMA accumulates into and
+// the epilogue re-zeroes after reading, full/empty ring barriers and tfull/tempty accumulator
+// barriers.  What bounds it at the full-resolution Cin = 8 layers is the TMA brick-fetch rate
+// times the halo amplification (profiles/r2_tma_box_rate.txt, profiles/r2_k2_n8_stalls.txt).
 #include <stdlib.h>
 
 #include <algorithm>
